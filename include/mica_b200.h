@@ -1,0 +1,166 @@
+/* mica_b200 -- C ABI of the B200-native voxel-parallel map pipeline.
+ *
+ * The reference (jianlin-cheng/MICA) has no FFI: its seam is three Python classes
+ * (SURVEY.md section 8b).  This header is the boundary our host-side mirrors of
+ * those classes bind through ctypes (mica_b200/_lib.py); each entry point cites the
+ * reference lines whose arithmetic it replaces (paths relative to the reference
+ * root).  Conventions: plain pointers and sizes only; every pointer documented
+ * "device" is CUDA device memory owned by the caller; the caller owns the stream
+ * (a cudaStream_t passed as void*); no hidden allocations (workspaces are sized
+ * by the *_workspace_bytes queries); functions return 0 or a negative MICA_ERR_*
+ * and never throw; launches are asynchronous unless stated otherwise; one host
+ * thread per GPU.  There is no CPU fallback.
+ *
+ * Index conventions: map volumes are (nz,ny,nx) C-order float32 exactly as
+ * mrcfile exposes them; "cube space" is the reference's transposed view
+ * (utils/create_grids.py:119-122) in which stitched volumes are indexed [x,y,z].
+ * Slab arguments (z0, nz_local) describe the contiguous range of memory-axis-0
+ * planes a rank holds when the volume is z-slab partitioned; a
+ * single GPU passes z0=0, nz_local=nz.
+ */
+#ifndef MICA_B200_H
+#define MICA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mica_stream_t; /* cudaStream_t */
+
+#define MICA_OK 0
+#define MICA_ERR_INVALID (-1)   /* bad argument */
+#define MICA_ERR_CUDA (-2)      /* CUDA runtime error, see mica_last_error() */
+#define MICA_ERR_WORKSPACE (-3) /* workspace too small */
+#define MICA_ERR_NO_DEVICE (-4) /* no CUDA device / driver: the library never falls back to the CPU */
+
+/* status word of the normaliser (mica_select_result) */
+#define MICA_NORM_OK 0
+#define MICA_NORM_NO_POSITIVE 1 /* utils/preprocessing.py:155-157 */
+#define MICA_NORM_ZERO_PCTL 2   /* utils/preprocessing.py:152-154 */
+#define MICA_NORM_PENDING 3     /* selection not finished */
+
+#define MICA_SELECT_HIST_WORDS 4096 /* int64 words the histogram all-reduce covers */
+#define MICA_SELECT_PASSES 5        /* hist/pick rounds for median + percentile */
+
+int mica_version(void);
+const char* mica_last_error(void);
+/* number of CUDA devices visible, or MICA_ERR_NO_DEVICE */
+int mica_device_count(void);
+/* kernels launched by this library in this process since load (for bench.py's gpu_launches) */
+int64_t mica_launch_count(void);
+
+/* ---------------------------------------------------------------- R1 resample
+ * Replaces scipy.ndimage.zoom(data, [vx,vy,vz], order=3) at
+ * utils/preprocessing.py:117 and scripts_for_training_data/create_normalized_map.py:43
+ * (mode='constant', cval=0, prefilter=True, grid_mode=False): cubic B-spline
+ * prefilter with mirror boundaries in float64, align-corners coordinate map,
+ * 64-tap gather, float32 result.  order=1 is the north-star trilinear variant
+ * (no prefilter).  zoom == (1,1,1) is SciPy's early-exit copy.
+ */
+/* host: out[a] = int(round(float32(in[a]) * zoom[a])), banker's rounding */
+int mica_zoom_output_shape(const int in_zyx[3], const float zoom_zyx[3], int out_zyx[3]);
+
+/* workspace for a source slab of src_nz_local planes */
+size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, int ny, int nx, int order);
+
+/* src: device float32 [src_nz_local, sy, sx] = global source planes [src_z0, src_z0+src_nz_local)
+ * dst: device float32 [dst_nz_local, ny, nx] = global output planes [dst_z0, dst_z0+dst_nz_local)
+ * (sz,sy,sx) / (nz,ny,nx) are the GLOBAL source / output shapes.  With a partial
+ * slab the z prefilter is run on the slab alone (mirror at its ends); the caller
+ * supplies >= 16 halo planes beyond the taps it needs (error < 1e-9).
+ */
+int mica_bspline_resample_f32(const float* src, int sz, int sy, int sx, int src_z0, int src_nz_local,
+                              float* dst, int nz, int ny, int nx, int dst_z0, int dst_nz_local,
+                              void* workspace, size_t workspace_bytes, int order, mica_stream_t stream);
+
+/* ------------------------------------------------------- R2/R3 normalisation
+ * Replaces np.nan_to_num / np.median / np.percentile(pos, 99.9) / clip / divide
+ * at utils/preprocessing.py:122-133 (twin: create_normalized_map.py:48-79) with
+ * an exact 3-pass (11/11/10-bit) radix select over order-preserving uint32 keys,
+ * following the installed NumPy 2.x float32 semantics.
+ * State lives in a device workspace so that multi-GPU runs can all-reduce the
+ * histogram (MICA_SELECT_HIST_WORDS int64 at mica_select_hist_ptr) between
+ * mica_select_hist and mica_select_pick without a host round trip.
+ * Protocol: init; repeat MICA_SELECT_PASSES times { hist; [all-reduce]; pick }.
+ */
+size_t mica_select_workspace_bytes(void);
+int mica_select_init(void* workspace, int64_t n_total, mica_stream_t stream);
+int mica_select_hist(const float* x, int64_t n_local, void* workspace, mica_stream_t stream);
+int64_t* mica_select_hist_ptr(void* workspace);
+int mica_select_pick(void* workspace, mica_stream_t stream);
+/* all five rounds on one GPU */
+int mica_order_stats_f32(const float* x, int64_t n, void* workspace, mica_stream_t stream);
+/* synchronises the stream; any out pointer may be NULL */
+int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
+                       mica_stream_t stream);
+/* y = min(m, p)/p with m = (x > med) * (x - med), written exactly as
+ * utils/preprocessing.py:124,131-133 evaluates it in float32; x == y allowed.
+ * Reads median / percentile from the workspace on the device; leaves y untouched
+ * when the status is not MICA_NORM_OK. */
+int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* workspace, mica_stream_t stream);
+
+/* ------------------------------------------------------------ R4 AF3 encoder
+ * Replaces transform_coordinates + the per-atom loop at
+ * utils/preprocessing.py:172-178,275-298 (twin: create_AF3_encodings.py:52-106).
+ * idx = clip(rint(coord - origin), 0, clip_hi) per (x,y,z); the reference passes
+ * clip_hi = (nz-1, ny-1, nx-1) -- i.e. in (z,y,x) order against (x,y,z) indices
+ * (quirk D7) -- so the three bounds are explicit.  vol24[ch, z, y, x] = 1.0 for the
+ * backbone channel (bb_ch 0..3 or -1) and the residue channel (aa_ch 4..23 or -1).
+ * vol24: device float32 [24, nz_local, ny, nx], zero-filled here.  *status_oob
+ * (device int) is set to 1 if any clipped index still exceeds its real axis (the
+ * reference then raises IndexError and returns False, :344-347); atoms whose z
+ * falls outside the slab are skipped silently.
+ */
+int mica_af3_encode(const float* xyz, const int8_t* bb_ch, const int8_t* aa_ch, int64_t n_atoms,
+                    float ox, float oy, float oz, int clip_x, int clip_y, int clip_z,
+                    int nz, int ny, int nx, int z0, int nz_local,
+                    float* vol24, int* status_oob, mica_stream_t stream);
+
+/* --------------------------------------------------------- R5/R6 cube extract
+ * Replaces GridCreator.transpose + create_grids_from_mrc (utils/create_grids.py:67-176),
+ * its training twins (scripts_for_training_data/create_grids_for_*.py) and the
+ * per-cube re-assembly of CryoEMTestDataset.__getitem__ (dataset/dataset.py:194-224):
+ * out[b, c, u0,u1,u2] = T_c[i_b-pad+u0, j_b-pad+u1, k_b-pad+u2] (0 outside T),
+ * T_c = transpose(vol_c, perm).  W = grid_size + 2*padding.
+ * vol: device float32, channel c at vol + c*chan_stride, each [nz_local, ny, nx]
+ * holding global planes [z0, z0+nz_local).  ijk: device int32 [B,3] cube origins
+ * in cube space.  out: device, cube b / channel c at out + b*out_cube_stride + c*W^3.
+ * nonzero (device int32 [B], nullable): OR-ed with 1 if cube b has any non-zero
+ * voxel in these channels (D8 routing; also the training twin's max >= 0.01 test
+ * is served by cube_max).  cube_max (device float32 [B], nullable, channel 0 only).
+ */
+int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_channels,
+                       int nz, int ny, int nx, int z0, int nz_local, const int perm[3],
+                       int grid_size, int padding, const int32_t* ijk, int n_cubes,
+                       float* out, int64_t out_cube_stride, int32_t* nonzero, float* cube_max,
+                       mica_stream_t stream);
+
+/* ------------------------------------------------ R7/R8 post-process + stitch
+ * Replaces the softmax/argmax block of run_inference (utils/predict.py:342-349)
+ * and reconstruct_volume (utils/predict.py:439-512) in one pass over the cube
+ * cores: bb = softmax(bb[{0,2,3}])[2]; ca likewise; aa_prob = softmax(aa[1:21]);
+ * aa_pred = argmax(aa_prob) stored as float32 (:462).  Cores are disjoint, so no
+ * atomics.  bb, ca: device [B,4,W^3]; aa: device [B,21,W^3]; ijk device int32
+ * [B,3].  Volumes are cube-space boxes: global shape (X,Y,Z), this rank holding
+ * [org0,org0+ext0) x [org1,..) x [org2,..) in C order; cores are clipped to it.
+ * aa_prob_vol: [20, ext0, ext1, ext2].
+ */
+int mica_postproc_stitch(const float* bb, const float* ca, const float* aa,
+                         const int32_t* ijk, int n_cubes, int X, int Y, int Z,
+                         const int org[3], const int ext[3], int grid_size, int padding,
+                         float* bb_vol, float* ca_vol, float* aa_prob_vol, float* aa_pred_vol,
+                         mica_stream_t stream);
+
+/* plain centre-crop paste of already post-processed cubes (reconstruct_volume on
+ * its own, utils/predict.py:494-501): cubes device [B, n_ch, W^3] -> vol [n_ch, ext...] */
+int mica_stitch_cubes(const float* cubes, int n_ch, const int32_t* ijk, int n_cubes,
+                      int X, int Y, int Z, const int org[3], const int ext[3],
+                      int grid_size, int padding, float* vol, mica_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICA_B200_H */

@@ -1,0 +1,80 @@
+"""ctypes binding of libmica_b200.so (the C ABI in include/mica_b200.h).
+
+There is no CPU fallback: importing this module raises if the library has not
+been built (``python -m mica_b200.build``), and every op raises if the CUDA
+driver / a GPU is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmica_b200.so')
+
+MICA_OK = 0
+ERR_NAMES = {-1: 'MICA_ERR_INVALID', -2: 'MICA_ERR_CUDA', -3: 'MICA_ERR_WORKSPACE', -4: 'MICA_ERR_NO_DEVICE'}
+NORM_OK, NORM_NO_POSITIVE, NORM_ZERO_PCTL, NORM_PENDING = 0, 1, 2, 3
+SELECT_HIST_WORDS = 4096
+SELECT_PASSES = 5
+
+
+class MicaError(RuntimeError):
+    pass
+
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f'{LIB_PATH} is missing: build it with `python -m mica_b200.build` '
+        '(or __graft_entry__.build()). mica_b200 has no CPU fallback.')
+
+lib = C.CDLL(LIB_PATH)
+
+_p, _i, _i64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+_I3 = C.c_int * 3
+_F3 = C.c_float * 3
+
+#: every symbol include/mica_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    'mica_version': (_i, []),
+    'mica_last_error': (C.c_char_p, []),
+    'mica_device_count': (_i, []),
+    'mica_launch_count': (_i64, []),
+    'mica_zoom_output_shape': (_i, [C.POINTER(_i), C.POINTER(_f), C.POINTER(_i)]),
+    'mica_resample_workspace_bytes': (_sz, [_i] * 7),
+    'mica_bspline_resample_f32': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
+    'mica_select_workspace_bytes': (_sz, []),
+    'mica_select_init': (_i, [_p, _i64, _p]),
+    'mica_select_hist': (_i, [_p, _i64, _p, _p]),
+    'mica_select_hist_ptr': (_p, [_p]),
+    'mica_select_pick': (_i, [_p, _p]),
+    'mica_order_stats_f32': (_i, [_p, _i64, _p, _p]),
+    'mica_select_result': (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(_i), _p]),
+    'mica_normalize_apply_f32': (_i, [_p, _p, _i64, _p, _p]),
+    'mica_af3_encode': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    'mica_extract_cubes': (_i, [_p, _i64, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i, _p, _i, _p, _i64,
+                                _p, _p, _p]),
+    'mica_postproc_stitch': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i,
+                                  _p, _p, _p, _p, _p]),
+    'mica_stitch_cubes': (_i, [_p, _i, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)          # AttributeError here == header / library mismatch
+    _fn.restype, _fn.argtypes = _res, _args
+
+
+def last_error() -> str:
+    return lib.mica_last_error().decode('utf-8', 'replace')
+
+
+def check(rc: int, what: str = ''):
+    if rc != MICA_OK:
+        raise MicaError(f'{what or "mica call"} failed: {ERR_NAMES.get(rc, rc)}: {last_error()}')
+
+
+def int3(v):
+    return _I3(int(v[0]), int(v[1]), int(v[2]))
+
+
+def float3(v):
+    return _F3(float(v[0]), float(v[1]), float(v[2]))

@@ -1,0 +1,58 @@
+"""In-tree build of the CUDA library (sm_100a only).
+
+    python -m mica_b200.build [--force] [--verbose]
+
+Produces mica_b200/libmica_b200.so with nvcc; the .so is git-ignored but travels
+to the GPU box with the snapshot.  No fast-math: the normaliser relies on IEEE
+float32 add / mul / div and on denormals."""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libmica_b200.so')
+
+NVCC_FLAGS = [
+    '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
+    '--ftz=false', '--prec-div=true', '--prec-sqrt=true',
+    '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-shared',
+]
+
+
+def sources():
+    return sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+
+
+def _stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = sources() + glob.glob(os.path.join(CSRC, '*.cuh')) + \
+        glob.glob(os.path.join(HERE, '..', 'include', '*.h'))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu under csrc/ into libmica_b200.so (no-op when up to date)."""
+    if not force and not _stale():
+        return LIB
+    nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
+    if not os.path.exists(nvcc):
+        raise RuntimeError('nvcc not found: cannot build libmica_b200.so')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB + '.tmp'] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed building libmica_b200.so')
+    os.replace(LIB + '.tmp', LIB)
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

@@ -1,0 +1,64 @@
+// Shared helpers for the mica_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/mica_b200.h"
+
+namespace mica {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+extern thread_local char g_last_error[512];
+extern std::atomic<int64_t> g_launches;
+
+int set_error(int code, const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+#define MICA_CUDA(call)                                      \
+  do {                                                       \
+    int _rc = ::mica::check_cuda((call), #call);             \
+    if (_rc != MICA_OK) return _rc;                          \
+  } while (0)
+
+#define MICA_LAUNCH_CHECK(name)                              \
+  do {                                                       \
+    ::mica::count_launch();                                  \
+    int _rc = ::mica::check_cuda(cudaGetLastError(), name);  \
+    if (_rc != MICA_OK) return _rc;                          \
+  } while (0)
+
+#define MICA_REQUIRE(cond, ...)                                            \
+  do {                                                                     \
+    if (!(cond)) return ::mica::set_error(MICA_ERR_INVALID, __VA_ARGS__);  \
+  } while (0)
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// streaming (read-once / write-once) accesses: keep L1 for the data with reuse
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream4(float4* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+}  // namespace mica

@@ -1,0 +1,410 @@
+// R2/R3: exact median / 99.9-percentile normalisation.
+//
+// Replaces utils/preprocessing.py:122-133 (reference root):
+//   norm = nan_to_num(x); med = np.median(norm); m = (norm > med) * (norm - med)
+//   p = np.percentile(m[m > 0], 99.9); m = min(m, p) / p
+// np.median / np.percentile are exact order statistics; they are found here by a
+// most-significant-digit radix select (11 + 11 + 10 bits) over order-preserving
+// uint32 keys with warp-ballot (match_any) aggregated shared-memory histograms.
+// The interpolation between the two bracketing order statistics follows the
+// installed NumPy 2.x float32 arithmetic.  Because float32
+// subtraction is monotone, the percentile of the positives m is selected on x at
+// rank count(x <= med) + lo and the median subtracted afterwards.
+//
+// All state lives in a device workspace; the host only sequences launches, so a
+// multi-GPU run can all-reduce hist[] between `hist` and `pick` on the stream.
+#include "common.cuh"
+
+namespace mica {
+
+constexpr int kBins = 2048;
+
+struct SelectState {
+  // histograms first: this is the region the multi-GPU all-reduce covers
+  long long hist[2][kBins];   // MICA_SELECT_HIST_WORDS int64
+  long long hist0[kBins];     // saved digit-0 histogram of the whole array
+  long long n_total;
+  long long rank[2];          // remaining rank of each target inside its prefix bucket
+  long long below[2];         // number of keys strictly below the prefix bucket
+  long long count_eq[2];      // multiplicity of the selected key (after the last pass)
+  unsigned prefix[2];         // key bits fixed so far (right-aligned)
+  int round;                  // 0..4 = next hist/pick round; 5 = done
+  int status;                 // MICA_NORM_*
+  long long n_le_med;         // count(x <= median)
+  long long n_pos;            // count(x > median)
+  float median;
+  float p;
+  float g;                    // percentile interpolation weight
+  int pad;
+};
+
+static_assert(sizeof(long long) * 2 * kBins == MICA_SELECT_HIST_WORDS * 8, "hist words");
+
+__device__ __forceinline__ float nan_to_num_f32(float v) {
+  // np.nan_to_num defaults: nan -> 0, +inf -> FLT_MAX, -inf -> -FLT_MAX
+  if (v != v) return 0.0f;
+  if (v == __int_as_float(0x7f800000)) return __int_as_float(0x7f7fffff);
+  if (v == __int_as_float(0xff800000)) return __int_as_float(0xff7fffff);
+  return v;
+}
+
+// order-preserving key; -0.0 and +0.0 share a key (they compare equal in NumPy's sort)
+__device__ __forceinline__ unsigned f32_key(float v) {
+  unsigned u = __float_as_uint(v);
+  if (u == 0x80000000u) u = 0u;
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(unsigned k) {
+  unsigned u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+  return __uint_as_float(u);
+}
+
+// round r -> which digit: rounds 0,1,2 = median digits 0,1,2; rounds 3,4 = percentile digits 1,2
+__device__ __forceinline__ int round_digit(int r) { return r < 3 ? r : r - 2; }
+
+__device__ __forceinline__ void warp_hist_add(unsigned* h, unsigned bin, bool pred) {
+  unsigned act = __ballot_sync(0xffffffffu, pred);
+  if (pred) {
+    unsigned peers = __match_any_sync(act, bin);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+  }
+}
+
+__device__ __forceinline__ void hist_one(float v, int digit, unsigned p0, unsigned p1, bool same, unsigned* h) {
+  unsigned k = f32_key(nan_to_num_f32(v));
+  if (digit == 0) {
+    warp_hist_add(h, k >> 21, true);
+  } else if (digit == 1) {
+    unsigned hi = k >> 21, bin = (k >> 10) & 0x7ffu;
+    warp_hist_add(h, bin, hi == p0);
+    if (!same) warp_hist_add(h + kBins, bin, hi == p1);
+  } else {
+    unsigned hi = k >> 10, bin = k & 0x3ffu;
+    warp_hist_add(h, bin, hi == p0);
+    if (!same) warp_hist_add(h + kBins, bin, hi == p1);
+  }
+}
+
+// persistent grid-stride histogram pass; float4 loads when aligned
+__global__ void __launch_bounds__(512)
+select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
+  __shared__ unsigned h[2 * kBins];
+  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const int round = s->round;
+  if (round >= MICA_SELECT_PASSES || s->status != MICA_NORM_PENDING) return;
+  const int digit = round_digit(round);
+  const unsigned p0 = s->prefix[0], p1 = s->prefix[1];
+  const bool same = (p0 == p1);
+
+  const long long n4 = (((uintptr_t)x & 15) == 0) ? (n >> 2) : 0;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // whole warps iterate together (match_any needs converged lanes): pad the loop to the warp
+  const long long n4_pad = (n4 + 31) & ~31LL;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4_pad; i += stride) {
+    bool ok = i < n4;
+    float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (__ballot_sync(0xffffffffu, ok) == 0xffffffffu) {
+      hist_one(v.x, digit, p0, p1, same, h);
+      hist_one(v.y, digit, p0, p1, same, h);
+      hist_one(v.z, digit, p0, p1, same, h);
+      hist_one(v.w, digit, p0, p1, same, h);
+    } else if (ok) {  // ragged last warp: plain atomics
+      float vv[4] = {v.x, v.y, v.z, v.w};
+      for (int c = 0; c < 4; ++c) {
+        unsigned k = f32_key(nan_to_num_f32(vv[c]));
+        if (digit == 0) {
+          atomicAdd(&h[k >> 21], 1u);
+        } else {
+          unsigned hi = digit == 1 ? (k >> 21) : (k >> 10);
+          unsigned bin = digit == 1 ? ((k >> 10) & 0x7ffu) : (k & 0x3ffu);
+          if (hi == p0) atomicAdd(&h[bin], 1u);
+          if (!same && hi == p1) atomicAdd(&h[kBins + bin], 1u);
+        }
+      }
+    }
+  }
+  // scalar tail (and the whole array when it is not 16-byte aligned)
+  for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    unsigned k = f32_key(nan_to_num_f32(x[i]));
+    if (digit == 0) {
+      atomicAdd(&h[k >> 21], 1u);
+    } else {
+      unsigned hi = digit == 1 ? (k >> 21) : (k >> 10);
+      unsigned bin = digit == 1 ? ((k >> 10) & 0x7ffu) : (k & 0x3ffu);
+      if (hi == p0) atomicAdd(&h[bin], 1u);
+      if (!same && hi == p1) atomicAdd(&h[kBins + bin], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) {
+    unsigned c = h[i];
+    if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[0][0]) + i, (unsigned long long)c);
+  }
+}
+
+// 1 block x kPickThreads threads, two bins per thread.  Finds the bucket holding `rank`.
+constexpr int kPickThreads = kBins / 2;
+
+__device__ void pick_bucket(const long long* hist, long long rank, int* bucket, long long* below,
+                            long long* count, long long* scratch /* [kPickThreads] shared */) {
+  const int t = threadIdx.x;
+  const long long v0 = hist[2 * t], v1 = hist[2 * t + 1];
+  scratch[t] = v0 + v1;
+  __syncthreads();
+  for (int off = 1; off < kPickThreads; off <<= 1) {  // Hillis-Steele inclusive scan
+    long long add = (t >= off) ? scratch[t - off] : 0;
+    __syncthreads();
+    scratch[t] += add;
+    __syncthreads();
+  }
+  const long long excl0 = scratch[t] - v0 - v1, excl1 = excl0 + v0;
+  if (v0 > 0 && rank >= excl0 && rank < excl0 + v0) {
+    *bucket = 2 * t;
+    *below = excl0;
+    *count = v0;
+  }
+  if (v1 > 0 && rank >= excl1 && rank < excl1 + v1) {
+    *bucket = 2 * t + 1;
+    *below = excl1;
+    *count = v1;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPickThreads)
+select_pick_kernel(SelectState* s) {
+  __shared__ long long scratch[kPickThreads];
+  __shared__ int bucket[2];
+  __shared__ long long below[2], count[2];
+  const int round = s->round;
+  if (round >= MICA_SELECT_PASSES || s->status != MICA_NORM_PENDING) return;
+  const int digit = round_digit(round);
+  const bool same = (s->prefix[0] == s->prefix[1]);
+  if (threadIdx.x < 2) {
+    bucket[threadIdx.x] = -1;
+    below[threadIdx.x] = 0;
+    count[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  if (round == 0) {  // keep the digit-0 histogram for the percentile phase
+    s->hist0[threadIdx.x] = s->hist[0][threadIdx.x];
+    s->hist0[threadIdx.x + kPickThreads] = s->hist[0][threadIdx.x + kPickThreads];
+  }
+  for (int t = 0; t < 2; ++t) {
+    const long long* h = (digit == 0 || same) ? s->hist[0] : s->hist[t];
+    pick_bucket(h, s->rank[t], &bucket[t], &below[t], &count[t], scratch);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2; ++t) {
+      int b = bucket[t] < 0 ? 0 : bucket[t];  // unreachable for consistent counts
+      s->prefix[t] = digit == 0 ? (unsigned)b : ((s->prefix[t] << (digit == 1 ? 11 : 10)) | (unsigned)b);
+      s->rank[t] -= below[t];
+      s->below[t] += below[t];
+      s->count_eq[t] = count[t];
+    }
+    if (round == 2) {
+      // ---- median (np.median on float32): N odd -> s[N/2]; N even -> f32((a + b) / 2)
+      float a = key_f32(s->prefix[0]), b = key_f32(s->prefix[1]);
+      float med = (s->n_total & 1) ? b : __fdiv_rn(__fadd_rn(a, b), 2.0f);
+      s->median = med;
+      // count(x <= med): a and b are adjacent order statistics, a <= med <= b
+      long long n_le = (med >= b) ? s->below[1] + s->count_eq[1] : s->below[0] + s->count_eq[0];
+      s->n_le_med = n_le;
+      long long npos = s->n_total - n_le;
+      s->n_pos = npos;
+      if (npos <= 0) {
+        s->status = MICA_NORM_NO_POSITIVE;
+        s->round = MICA_SELECT_PASSES;
+      } else {
+        // ---- np.percentile(pos, 99.9), float32 virtual index (NumPy >= 2)
+        float q = __fdiv_rn(99.9f, 100.0f);
+        float vi = __fmul_rn((float)(npos - 1), q);
+        float prev = floorf(vi);
+        float next = __fadd_rn(prev, 1.0f);
+        long long lo, hi;
+        if (vi >= (float)(npos - 1)) {
+          lo = hi = npos - 1;
+        } else {
+          lo = (long long)prev;
+          hi = (long long)next;
+        }
+        if (hi > npos - 1) hi = npos - 1;
+        s->g = __fsub_rn(vi, prev);
+        s->rank[0] = n_le + lo;
+        s->rank[1] = n_le + hi;
+        s->below[0] = s->below[1] = 0;
+        s->prefix[0] = s->prefix[1] = 0;
+      }
+    } else if (round == 4) {
+      float med = s->median;
+      float a = __fsub_rn(key_f32(s->prefix[0]), med);
+      float b = __fsub_rn(key_f32(s->prefix[1]), med);
+      float g = s->g;
+      float d = __fsub_rn(b, a);
+      float r = __fadd_rn(a, __fmul_rn(d, g));
+      if (g >= 0.5f) r = __fsub_rn(b, __fmul_rn(d, __fsub_rn(1.0f, g)));
+      s->p = r;
+      s->status = (r != 0.0f) ? MICA_NORM_OK : MICA_NORM_ZERO_PCTL;
+    }
+    if (s->round < MICA_SELECT_PASSES) s->round = round + 1;
+  }
+  __syncthreads();
+  // clear the exchange histograms for the next round
+  for (int i = threadIdx.x; i < kBins; i += kPickThreads) {
+    s->hist[0][i] = 0;
+    s->hist[1][i] = 0;
+  }
+  __syncthreads();
+  if (round == 2 && s->status == MICA_NORM_PENDING) {
+    // percentile digit 0 comes from the saved whole-array histogram (no extra data pass)
+    __shared__ int b2[2];
+    __shared__ long long bl2[2], c2[2];
+    for (int t = 0; t < 2; ++t) pick_bucket(s->hist0, s->rank[t], &b2[t], &bl2[t], &c2[t], scratch);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int t = 0; t < 2; ++t) {
+        s->prefix[t] = (unsigned)b2[t];
+        s->rank[t] -= bl2[t];
+        s->below[t] = bl2[t];
+        s->count_eq[t] = c2[t];
+      }
+    }
+  }
+}
+
+__global__ void select_init_kernel(SelectState* s, long long n_total) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < kBins) {
+    s->hist[0][t] = 0;
+    s->hist[1][t] = 0;
+    s->hist0[t] = 0;
+  }
+  if (t == 0) {
+    s->n_total = n_total;
+    // np.median: order statistics (N-1)/2 and N/2 (equal when N is odd)
+    s->rank[0] = (n_total - 1) / 2;
+    s->rank[1] = n_total / 2;
+    s->below[0] = s->below[1] = 0;
+    s->count_eq[0] = s->count_eq[1] = 0;
+    s->prefix[0] = s->prefix[1] = 0;
+    s->round = 0;
+    s->status = n_total > 0 ? MICA_NORM_PENDING : MICA_NORM_NO_POSITIVE;
+    s->n_le_med = 0;
+    s->n_pos = 0;
+    s->median = 0.f;
+    s->p = 0.f;
+    s->g = 0.f;
+  }
+}
+
+// y = ((m < p) * m + (m >= p) * p) / p,  m = (v > med) * (v - med): every product and
+// sum is a separate IEEE float32 operation, exactly as NumPy evaluates the expression
+__device__ __forceinline__ float normalize_one(float x, float med, float p) {
+  float v = nan_to_num_f32(x);
+  float m = __fmul_rn((v > med) ? 1.0f : 0.0f, __fsub_rn(v, med));
+  float r = __fadd_rn(__fmul_rn((m < p) ? 1.0f : 0.0f, m), __fmul_rn((m >= p) ? 1.0f : 0.0f, p));
+  return __fdiv_rn(r, p);
+}
+
+__global__ void __launch_bounds__(256)
+normalize_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
+                       const SelectState* __restrict__ s) {
+  if (s->status != MICA_NORM_OK) return;
+  const float med = s->median, p = s->p;
+  const bool vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
+  const long long n4 = vec ? (n >> 2) : 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (long long i = tid; i < n4; i += stride) {
+    float4 v = x4[i];
+    v.x = normalize_one(v.x, med, p);
+    v.y = normalize_one(v.y, med, p);
+    v.z = normalize_one(v.z, med, p);
+    v.w = normalize_one(v.w, med, p);
+    y4[i] = v;
+  }
+  for (long long i = n4 * 4 + tid; i < n; i += stride) y[i] = normalize_one(x[i], med, p);
+}
+
+}  // namespace mica
+
+using namespace mica;
+
+extern "C" size_t mica_select_workspace_bytes(void) { return sizeof(SelectState) + 256; }
+
+static SelectState* state_of(const void* ws) { return (SelectState*)(((uintptr_t)ws + 255) / 256 * 256); }
+
+extern "C" int64_t* mica_select_hist_ptr(void* workspace) {
+  return workspace ? (int64_t*)&state_of(workspace)->hist[0][0] : nullptr;
+}
+
+extern "C" int mica_select_init(void* workspace, int64_t n_total, mica_stream_t stream) {
+  MICA_REQUIRE(workspace, "null workspace");
+  MICA_REQUIRE(n_total >= 0, "negative n");
+  select_init_kernel<<<kBins / 256, 256, 0, (cudaStream_t)stream>>>(state_of(workspace), n_total);
+  MICA_LAUNCH_CHECK("select_init_kernel");
+  return MICA_OK;
+}
+
+extern "C" int mica_select_hist(const float* x, int64_t n_local, void* workspace, mica_stream_t stream) {
+  MICA_REQUIRE(workspace && (x || n_local == 0), "null pointer");
+  MICA_REQUIRE(n_local >= 0, "negative n");
+  if (n_local == 0) return MICA_OK;
+  int64_t want = ceil_div64(ceil_div64(n_local, 4), 512);
+  int grid = (int)(want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4);
+  select_hist_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(x, n_local, state_of(workspace));
+  MICA_LAUNCH_CHECK("select_hist_kernel");
+  return MICA_OK;
+}
+
+extern "C" int mica_select_pick(void* workspace, mica_stream_t stream) {
+  MICA_REQUIRE(workspace, "null workspace");
+  select_pick_kernel<<<1, kPickThreads, 0, (cudaStream_t)stream>>>(state_of(workspace));
+  MICA_LAUNCH_CHECK("select_pick_kernel");
+  return MICA_OK;
+}
+
+extern "C" int mica_order_stats_f32(const float* x, int64_t n, void* workspace, mica_stream_t stream) {
+  int rc = mica_select_init(workspace, n, stream);
+  for (int r = 0; r < MICA_SELECT_PASSES && rc == MICA_OK; ++r) {
+    rc = mica_select_hist(x, n, workspace, stream);
+    if (rc == MICA_OK) rc = mica_select_pick(workspace, stream);
+  }
+  return rc;
+}
+
+extern "C" int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
+                                  mica_stream_t stream) {
+  MICA_REQUIRE(workspace, "null workspace");
+  struct Tail {
+    long long n_le_med, n_pos;
+    float median, p, g;
+    int pad;
+  } tail;
+  int status = 0;
+  const SelectState* s = state_of(workspace);
+  cudaStream_t st = (cudaStream_t)stream;
+  MICA_CUDA(cudaMemcpyAsync(&tail, &s->n_le_med, sizeof(tail), cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaMemcpyAsync(&status, &s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaStreamSynchronize(st));
+  if (median) *median = tail.median;
+  if (p999) *p999 = tail.p;
+  if (n_pos) *n_pos = tail.n_pos;
+  if (norm_status) *norm_status = status;
+  return MICA_OK;
+}
+
+extern "C" int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* workspace, mica_stream_t stream) {
+  MICA_REQUIRE(x && y && workspace, "null pointer");
+  if (n <= 0) return MICA_OK;
+  int64_t want = ceil_div64(ceil_div64(n, 4), 256);
+  int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
+  normalize_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n, state_of(workspace));
+  MICA_LAUNCH_CHECK("normalize_apply_kernel");
+  return MICA_OK;
+}

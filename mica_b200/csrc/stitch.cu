@@ -1,0 +1,192 @@
+// R7/R8: fused softmax / argmax post-processing and volume stitching.
+//
+// Replaces, in one pass over the model's logits, the block at utils/predict.py:342-349
+// (reference root)
+//     bb = softmax(cat(bb[:, :1], bb[:, 2:]))[:, 2]        (3-way, class 1 dropped)
+//     ca = softmax(cat(ca[:, :1], ca[:, 2:]))[:, 2]
+//     aa_scores = softmax(aa[:, 1:]); aa_pred = argmax(aa_scores)
+// the per-cube .cpu().numpy() + np.savez round trip (:353-369) and reconstruct_volume
+// (:439-512): vol[i:i+di, j:j+dj, k:k+dk] = cube[pad:pad+di, pad:pad+dj, pad:pad+dk].
+// Only the disjoint cores are read (the halo predictions are discarded by the
+// reference too), so each output voxel is written exactly once: no atomics, no weights.
+// One thread per core voxel, the cube's fastest axis across the warp: 26 coalesced
+// channel reads (stride W^3) and 23 coalesced writes per voxel.
+#include "common.cuh"
+
+namespace mica {
+
+struct StitchParams {
+  const float* bb;
+  const float* ca;
+  const float* aa;
+  const int32_t* ijk;
+  int X, Y, Z;
+  int org[3], ext[3];
+  int S, pad, W;
+  float* bb_vol;
+  float* ca_vol;
+  float* aa_prob_vol;
+  float* aa_pred_vol;
+};
+
+__device__ __forceinline__ float softmax3_last(float l0, float l1, float l2) {
+  float m = fmaxf(l0, fmaxf(l1, l2));
+  float e0 = expf(l0 - m), e1 = expf(l1 - m), e2 = expf(l2 - m);
+  float s = __fadd_rn(__fadd_rn(e0, e1), e2);
+  return __fdiv_rn(e2, s);
+}
+
+// grid = (S [core plane a], B), block = 256
+__global__ void __launch_bounds__(256)
+postproc_stitch_kernel(StitchParams P) {
+  const int a = blockIdx.x, b = blockIdx.y;
+  const int S = P.S, W = P.W;
+  const int i = P.ijk[3 * b + 0], j = P.ijk[3 * b + 1], k = P.ijk[3 * b + 2];
+  const int gx = i + a;
+  if (gx >= P.X || gx < P.org[0] || gx >= P.org[0] + P.ext[0]) return;
+  const int64_t W3 = (int64_t)W * W * W;
+  const float* bb = P.bb + (int64_t)b * 4 * W3;
+  const float* ca = P.ca + (int64_t)b * 4 * W3;
+  const float* aa = P.aa + (int64_t)b * 21 * W3;
+  const int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int bj = e / S, c = e - bj * S;
+    const int gy = j + bj, gz = k + c;
+    if (gy >= P.Y || gz >= P.Z) continue;
+    const int ly = gy - P.org[1], lz = gz - P.org[2];
+    if ((unsigned)ly >= (unsigned)P.ext[1] || (unsigned)lz >= (unsigned)P.ext[2]) continue;
+    const int64_t src = ((int64_t)(a + P.pad) * W + (bj + P.pad)) * W + (c + P.pad);
+    const int64_t dst = ((int64_t)(gx - P.org[0]) * P.ext[1] + ly) * P.ext[2] + lz;
+    // issue every load before the math: 26 independent requests in flight per thread
+    const float b0 = ld_stream(bb + src), b2 = ld_stream(bb + 2 * W3 + src), b3 = ld_stream(bb + 3 * W3 + src);
+    const float c0 = ld_stream(ca + src), c2 = ld_stream(ca + 2 * W3 + src), c3 = ld_stream(ca + 3 * W3 + src);
+    float l[20];
+#pragma unroll
+    for (int t = 0; t < 20; ++t) l[t] = ld_stream(aa + (int64_t)(t + 1) * W3 + src);
+    st_stream(P.bb_vol + dst, softmax3_last(b0, b2, b3));
+    st_stream(P.ca_vol + dst, softmax3_last(c0, c2, c3));
+    float m = l[0];
+#pragma unroll
+    for (int t = 1; t < 20; ++t) m = fmaxf(m, l[t]);
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 20; ++t) {
+      l[t] = expf(l[t] - m);
+      s = __fadd_rn(s, l[t]);
+    }
+    float best = -1.f;
+    int arg = 0;
+#pragma unroll
+    for (int t = 0; t < 20; ++t) {
+      const float p = __fdiv_rn(l[t], s);
+      st_stream(P.aa_prob_vol + (int64_t)t * vol_n + dst, p);
+      if (p > best) {  // first maximum wins, as torch.max
+        best = p;
+        arg = t;
+      }
+    }
+    st_stream(P.aa_pred_vol + dst, (float)arg);
+  }
+}
+
+// grid = (S, n_ch, B), block = 256: vol[ch, core] = cubes[b, ch, core]
+__global__ void __launch_bounds__(256)
+stitch_cubes_kernel(const float* __restrict__ cubes, int n_ch, const int32_t* __restrict__ ijk, int X, int Y,
+                    int Z, int o0, int o1, int o2, int e0, int e1, int e2, int S, int pad, int W,
+                    float* __restrict__ vol) {
+  const int a = blockIdx.x, ch = blockIdx.y, b = blockIdx.z;
+  const int i = ijk[3 * b + 0], j = ijk[3 * b + 1], k = ijk[3 * b + 2];
+  const int gx = i + a;
+  if (gx >= X || gx < o0 || gx >= o0 + e0) return;
+  const int64_t W3 = (int64_t)W * W * W;
+  const float* cube = cubes + ((int64_t)b * n_ch + ch) * W3;
+  float* v = vol + (int64_t)ch * e0 * e1 * e2;
+  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+    const int bj = e / S, c = e - bj * S;
+    const int gy = j + bj, gz = k + c;
+    if (gy >= Y || gz >= Z) continue;
+    const int ly = gy - o1, lz = gz - o2;
+    if ((unsigned)ly >= (unsigned)e1 || (unsigned)lz >= (unsigned)e2) continue;
+    const int64_t src = ((int64_t)(a + pad) * W + (bj + pad)) * W + (c + pad);
+    v[((int64_t)(gx - o0) * e1 + ly) * e2 + lz] = ld_stream(cube + src);
+  }
+}
+
+}  // namespace mica
+
+using namespace mica;
+
+static int check_box(int X, int Y, int Z, const int org[3], const int ext[3]) {
+  MICA_REQUIRE(org && ext, "null box");
+  MICA_REQUIRE(X > 0 && Y > 0 && Z > 0, "empty volume");
+  const int G[3] = {X, Y, Z};
+  for (int m = 0; m < 3; ++m)
+    MICA_REQUIRE(org[m] >= 0 && ext[m] > 0 && org[m] + ext[m] <= G[m], "box outside the volume on axis %d", m);
+  return MICA_OK;
+}
+
+extern "C" int mica_postproc_stitch(const float* bb, const float* ca, const float* aa,
+                                    const int32_t* ijk, int n_cubes, int X, int Y, int Z,
+                                    const int org[3], const int ext[3], int grid_size, int padding,
+                                    float* bb_vol, float* ca_vol, float* aa_prob_vol, float* aa_pred_vol,
+                                    mica_stream_t stream) {
+  MICA_REQUIRE(bb_vol && ca_vol && aa_prob_vol && aa_pred_vol, "null output volume");
+  MICA_REQUIRE(n_cubes == 0 || (bb && ca && aa && ijk), "null input");
+  MICA_REQUIRE(grid_size > 0 && padding >= 0, "bad grid_size/padding");
+  int rc = check_box(X, Y, Z, org, ext);
+  if (rc) return rc;
+  if (n_cubes <= 0) return MICA_OK;
+  StitchParams P;
+  P.bb = bb;
+  P.ca = ca;
+  P.aa = aa;
+  P.X = X;
+  P.Y = Y;
+  P.Z = Z;
+  for (int m = 0; m < 3; ++m) {
+    P.org[m] = org[m];
+    P.ext[m] = ext[m];
+  }
+  P.S = grid_size;
+  P.pad = padding;
+  P.W = grid_size + 2 * padding;
+  P.bb_vol = bb_vol;
+  P.ca_vol = ca_vol;
+  P.aa_prob_vol = aa_prob_vol;
+  P.aa_pred_vol = aa_pred_vol;
+  const int64_t W3 = (int64_t)P.W * P.W * P.W;
+  const int kMaxY = 32768;
+  for (int b0 = 0; b0 < n_cubes; b0 += kMaxY) {
+    const int nb = (n_cubes - b0 < kMaxY) ? n_cubes - b0 : kMaxY;
+    P.bb = bb + (int64_t)b0 * 4 * W3;
+    P.ca = ca + (int64_t)b0 * 4 * W3;
+    P.aa = aa + (int64_t)b0 * 21 * W3;
+    P.ijk = ijk + 3 * (int64_t)b0;
+    postproc_stitch_kernel<<<dim3(grid_size, nb), 256, 0, (cudaStream_t)stream>>>(P);
+    MICA_LAUNCH_CHECK("postproc_stitch_kernel");
+  }
+  return MICA_OK;
+}
+
+extern "C" int mica_stitch_cubes(const float* cubes, int n_ch, const int32_t* ijk, int n_cubes,
+                                 int X, int Y, int Z, const int org[3], const int ext[3],
+                                 int grid_size, int padding, float* vol, mica_stream_t stream) {
+  MICA_REQUIRE(vol, "null output volume");
+  MICA_REQUIRE(n_cubes == 0 || (cubes && ijk), "null input");
+  MICA_REQUIRE(n_ch > 0 && n_ch <= 65535, "bad channel count");
+  MICA_REQUIRE(grid_size > 0 && padding >= 0, "bad grid_size/padding");
+  int rc = check_box(X, Y, Z, org, ext);
+  if (rc) return rc;
+  if (n_cubes <= 0) return MICA_OK;
+  const int W = grid_size + 2 * padding;
+  const int64_t W3 = (int64_t)W * W * W;
+  const int kMaxZ = 32768;
+  for (int b0 = 0; b0 < n_cubes; b0 += kMaxZ) {
+    const int nb = (n_cubes - b0 < kMaxZ) ? n_cubes - b0 : kMaxZ;
+    stitch_cubes_kernel<<<dim3(grid_size, n_ch, nb), 256, 0, (cudaStream_t)stream>>>(
+        cubes + (int64_t)b0 * n_ch * W3, n_ch, ijk + 3 * (int64_t)b0, X, Y, Z, org[0], org[1], org[2], ext[0],
+        ext[1], ext[2], grid_size, padding, W, vol);
+    MICA_LAUNCH_CHECK("stitch_cubes_kernel");
+  }
+  return MICA_OK;
+}

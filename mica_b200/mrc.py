@@ -1,0 +1,80 @@
+"""MRC2014 reader/writer for the pipeline's on-disk products.
+
+Replaces the ``mrcfile`` calls at utils/preprocessing.py:98-107,138-148,196-206
+and utils/create_grids.py:108-117: float32 mode-2 maps, ``data`` shaped
+(nz,ny,nx), ``voxel_size = cella / m{x,y,z}`` as float32, origin / axis order /
+n*start carried through.  Pure I/O -- no arithmetic of the hot path lives here."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_MODES = {0: np.int8, 1: np.int16, 2: np.float32, 6: np.uint16, 12: np.float16}
+
+
+@dataclass
+class MrcMap:
+    data: np.ndarray                         # (nz, ny, nx)
+    voxel_size: tuple = (1.0, 1.0, 1.0)       # (x, y, z) as np.float32
+    origin: tuple = (0.0, 0.0, 0.0)           # (x, y, z) as np.float32
+    mapc: int = 1
+    mapr: int = 2
+    maps: int = 3
+    nxstart: int = 0
+    nystart: int = 0
+    nzstart: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+def read_mrc(path) -> MrcMap:
+    with open(path, 'rb') as f:
+        hdr = f.read(1024)
+        if len(hdr) < 1024:
+            raise ValueError(f'{path}: truncated MRC header')
+        w = np.frombuffer(hdr, dtype='<i4', count=56)
+        fl = np.frombuffer(hdr, dtype='<f4', count=56)
+        nx, ny, nz, mode = (int(v) for v in w[0:4])
+        if mode not in _MODES or min(nx, ny, nz) <= 0:
+            raise ValueError(f'{path}: unsupported MRC (mode={mode}, shape={(nz, ny, nx)})')
+        nsymbt = int(w[23])
+        f.seek(1024 + max(nsymbt, 0))
+        dt = np.dtype(_MODES[mode]).newbyteorder('<')
+        data = np.frombuffer(f.read(dt.itemsize * nx * ny * nz), dtype=dt)
+        if data.size != nx * ny * nz:
+            raise ValueError(f'{path}: truncated MRC payload')
+    mx, my, mz = (int(v) for v in w[7:10])
+    cella = fl[10:13]
+    f32 = np.float32
+    vs = tuple(f32(cella[a]) / f32(m) if m else f32(0) for a, m in enumerate((mx, my, mz)))
+    return MrcMap(data=data.reshape(nz, ny, nx), voxel_size=vs,
+                  origin=tuple(f32(v) for v in fl[49:52]),
+                  mapc=int(w[16]), mapr=int(w[17]), maps=int(w[18]),
+                  nxstart=int(w[4]), nystart=int(w[5]), nzstart=int(w[6]))
+
+
+def write_mrc(path, m: MrcMap):
+    data = np.ascontiguousarray(m.data, dtype='<f4')
+    nz, ny, nx = data.shape
+    hdr = np.zeros(256, dtype='<i4')
+    fl = hdr.view('<f4')
+    hdr[0:4] = (nx, ny, nz, 2)
+    hdr[4:7] = (m.nxstart, m.nystart, m.nzstart)
+    hdr[7:10] = (nx, ny, nz)
+    vx, vy, vz = (np.float32(v) for v in m.voxel_size)
+    fl[10:13] = (vx * nx, vy * ny, vz * nz)
+    fl[13:16] = 90.0
+    hdr[16:19] = (m.mapc, m.mapr, m.maps)
+    fl[19] = data.min() if data.size else 0
+    fl[20] = data.max() if data.size else 0
+    fl[21] = data.mean(dtype=np.float64) if data.size else 0
+    hdr[22] = 1
+    hdr[27] = 20140
+    fl[49:52] = [np.float32(v) for v in m.origin]
+    raw = bytearray(hdr.tobytes())
+    raw[208:212] = b'MAP '
+    raw[212:216] = bytes([0x44, 0x44, 0, 0])
+    raw[216:220] = np.float32(data.std(dtype=np.float64) if data.size else 0).tobytes()
+    with open(path, 'wb') as f:
+        f.write(bytes(raw))
+        f.write(data.tobytes())

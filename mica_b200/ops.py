@@ -1,0 +1,246 @@
+"""Torch-tensor front end of the C ABI (device pointers in, device tensors out).
+
+PyTorch is plumbing here -- it owns the HBM allocations and the stream; all the
+arithmetic of the hot path happens in libmica_b200.so.  Every function raises
+unless its tensors live on a CUDA device: there is no CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+STANDARD_PERM = (2, 1, 0)     # trans_order for mapc,mapr,maps = 1,2,3 (utils/create_grids.py:120-122)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev(t: torch.Tensor, dtype, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.MicaError(f'{name} must be a CUDA tensor (mica_b200 has no CPU fallback)')
+    if t.dtype != dtype:
+        raise _lib.MicaError(f'{name} must be {dtype}, got {t.dtype}')
+    if not t.is_contiguous():
+        raise _lib.MicaError(f'{name} must be contiguous')
+    return C.c_void_p(t.data_ptr())
+
+
+def require_gpu():
+    n = lib.mica_device_count()
+    if n < 0:
+        raise _lib.MicaError(f'no usable CUDA device: {_lib.last_error()}')
+    return n
+
+
+def launch_count() -> int:
+    return int(lib.mica_launch_count())
+
+
+# ------------------------------------------------------------------ R1 resample
+def zoom_output_shape(in_zyx, zoom_zyx):
+    """int(round(float32(n) * float32(zoom))) per axis (scipy.ndimage.zoom under NumPy 2)."""
+    out = (C.c_int * 3)()
+    check(lib.mica_zoom_output_shape(_lib.int3(in_zyx), _lib.float3(zoom_zyx), out), 'zoom_output_shape')
+    return tuple(int(v) for v in out)
+
+
+def resample(src: torch.Tensor, out_shape, order: int = 3, *, src_z0: int = 0, src_shape=None,
+             dst_z0: int = 0, dst_nz_local=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Cubic B-spline (order=3) / trilinear (order=1) resample of ``src`` (sz,sy,sx) to
+    the global shape ``out_shape``.  Slab form: ``src`` holds global planes
+    [src_z0, src_z0+len) of a (src_shape) volume; planes [dst_z0, dst_z0+dst_nz_local)
+    of the output are produced."""
+    p_src = _dev(src, torch.float32, 'src')
+    sz_l, sy, sx = src.shape
+    sz = int(src_shape[0]) if src_shape is not None else sz_l
+    nz, ny, nx = (int(v) for v in out_shape)
+    nzl = nz - dst_z0 if dst_nz_local is None else int(dst_nz_local)
+    if out is None:
+        out = torch.empty((nzl, ny, nx), dtype=torch.float32, device=src.device)
+    p_out = _dev(out, torch.float32, 'out')
+    if tuple(out.shape) != (nzl, ny, nx):
+        raise _lib.MicaError(f'out has shape {tuple(out.shape)}, expected {(nzl, ny, nx)}')
+    nbytes = lib.mica_resample_workspace_bytes(sz_l, sy, sx, nz, ny, nx, order)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=src.device)
+    check(lib.mica_bspline_resample_f32(p_src, sz, sy, sx, src_z0, sz_l, p_out, nz, ny, nx, dst_z0, nzl,
+                                        C.c_void_p(ws.data_ptr()), nbytes, order, _stream()), 'resample')
+    return out
+
+
+# --------------------------------------------------------------- R2/R3 normalise
+class OrderStats:
+    """Device-resident state of the exact radix select (median + 99.9 percentile)."""
+
+    def __init__(self, device):
+        self.ws = torch.zeros(lib.mica_select_workspace_bytes(), dtype=torch.uint8, device=device)
+        self._p = C.c_void_p(self.ws.data_ptr())
+
+    def hist_view(self) -> torch.Tensor:
+        """int64 view of the histogram words a multi-GPU run all-reduces between hist and pick."""
+        off = lib.mica_select_hist_ptr(self._p) - self.ws.data_ptr()
+        return self.ws[off:off + 8 * _lib.SELECT_HIST_WORDS].view(torch.int64)
+
+    def run(self, x: torch.Tensor, n_total: int | None = None, all_reduce=None):
+        """``all_reduce(hist_int64_tensor)`` is called between hist and pick when given
+        (multi-GPU: torch.distributed.all_reduce over NCCL on the current stream)."""
+        p_x = _dev(x, torch.float32, 'x')
+        n_local = x.numel()
+        n_total = n_local if n_total is None else int(n_total)
+        st = _stream()
+        if all_reduce is None:
+            check(lib.mica_order_stats_f32(p_x, n_local, self._p, st), 'order_stats')
+            return self
+        check(lib.mica_select_init(self._p, n_total, st), 'select_init')
+        hist = self.hist_view()
+        for _ in range(_lib.SELECT_PASSES):
+            check(lib.mica_select_hist(p_x, n_local, self._p, st), 'select_hist')
+            all_reduce(hist)
+            check(lib.mica_select_pick(self._p, st), 'select_pick')
+        return self
+
+    def result(self):
+        """(median, p999, n_pos, status) -- synchronises the stream."""
+        med, p, npos, status = C.c_float(), C.c_float(), C.c_int64(), C.c_int()
+        check(lib.mica_select_result(self._p, C.byref(med), C.byref(p), C.byref(npos), C.byref(status),
+                                     _stream()), 'select_result')
+        return np.float32(med.value), np.float32(p.value), int(npos.value), int(status.value)
+
+    def apply(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        p_x = _dev(x, torch.float32, 'x')
+        if out is None:
+            out = torch.zeros_like(x)
+        p_y = _dev(out, torch.float32, 'out')
+        check(lib.mica_normalize_apply_f32(p_x, p_y, x.numel(), self._p, _stream()), 'normalize_apply')
+        return out
+
+
+def normalize(x: torch.Tensor, inplace: bool = False):
+    """utils/preprocessing.py:122-133 on the device.  Returns (normalised, OrderStats)."""
+    st = OrderStats(x.device).run(x)
+    return st.apply(x, x if inplace else None), st
+
+
+# ---------------------------------------------------------------- R4 AF3 encode
+def af3_encode(coords: torch.Tensor, bb_ch: torch.Tensor, aa_ch: torch.Tensor, origin_xyz, shape_zyx,
+               clip_hi_xyz=None, *, z0: int = 0, nz_local=None, out: torch.Tensor | None = None):
+    """24-channel rasteriser.  ``clip_hi_xyz`` defaults to the reference's (quirky)
+    bounds (nz-1, ny-1, nx-1) applied to (x,y,z) (utils/preprocessing.py:177,294).
+    Returns (vol24 [24,nz_local,ny,nx], status int32 tensor[1]; 1 == IndexError path)."""
+    nz, ny, nx = (int(v) for v in shape_zyx)
+    if clip_hi_xyz is None:
+        clip_hi_xyz = (nz - 1, ny - 1, nx - 1)
+    nzl = nz - z0 if nz_local is None else int(nz_local)
+    n = coords.shape[0]
+    p_xyz = _dev(coords, torch.float32, 'coords') if n else None
+    p_bb = _dev(bb_ch, torch.int8, 'bb_ch') if n else None
+    p_aa = _dev(aa_ch, torch.int8, 'aa_ch') if n else None
+    dev = coords.device
+    if out is None:
+        out = torch.empty((24, nzl, ny, nx), dtype=torch.float32, device=dev)
+    p_out = _dev(out, torch.float32, 'out')
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    ox, oy, oz = (float(np.float32(v)) for v in origin_xyz)
+    check(lib.mica_af3_encode(p_xyz, p_bb, p_aa, n, ox, oy, oz, int(clip_hi_xyz[0]), int(clip_hi_xyz[1]),
+                              int(clip_hi_xyz[2]), nz, ny, nx, z0, nzl, p_out,
+                              C.c_void_p(status.data_ptr()), _stream()), 'af3_encode')
+    return out, status
+
+
+# ------------------------------------------------------------ R5/R6 cube extract
+def cube_space_shape(shape_zyx, perm=STANDARD_PERM):
+    return tuple(int(shape_zyx[p]) for p in perm)
+
+
+def cube_origins(cube_shape, grid_size):
+    """(i,j,k) in the loop order of utils/create_grids.py:143-145 -> int32 [n,3]."""
+    ax = [np.arange(0, int(s), grid_size, dtype=np.int32) for s in cube_shape]
+    g = np.stack(np.meshgrid(*ax, indexing='ij'), axis=-1).reshape(-1, 3)
+    return np.ascontiguousarray(g)
+
+
+def extract_cubes(vol: torch.Tensor, ijk: torch.Tensor, grid_size: int = 48, padding: int = 8,
+                  perm=STANDARD_PERM, *, global_nz=None, z0: int = 0, out: torch.Tensor | None = None,
+                  nonzero: torch.Tensor | None = None, cube_max: torch.Tensor | None = None):
+    """vol [C,nz_local,ny,nx] (or [nz,ny,nx]) -> out [B,C,W,W,W] for the cube origins ``ijk``
+    (int32 [B,3], cube space).  ``out`` may be a channel slice of a larger [B,Ctot,W,W,W]
+    buffer (only the batch stride may be non-dense)."""
+    if vol.dim() == 3:
+        vol = vol.unsqueeze(0)
+    p_vol = _dev(vol, torch.float32, 'vol')
+    Cn, nzl, ny, nx = vol.shape
+    nz = nzl if global_nz is None else int(global_nz)
+    p_ijk = _dev(ijk, torch.int32, 'ijk')
+    B = ijk.shape[0]
+    W = grid_size + 2 * padding
+    if out is None:
+        out = torch.empty((B, Cn, W, W, W), dtype=torch.float32, device=vol.device)
+    if not out.is_cuda or out.dtype != torch.float32 or tuple(out.shape) != (B, Cn, W, W, W):
+        raise _lib.MicaError(f'out must be a CUDA float32 [{B},{Cn},{W},{W},{W}] tensor')
+    if B and out.stride()[1:] != (W ** 3, W * W, W, 1):
+        raise _lib.MicaError('out must be dense in every axis but the batch')
+    cube_stride = out.stride(0) if B else Cn * W ** 3
+    p_nz = _dev(nonzero, torch.int32, 'nonzero') if nonzero is not None else None
+    p_mx = _dev(cube_max, torch.float32, 'cube_max') if cube_max is not None else None
+    check(lib.mica_extract_cubes(p_vol, vol.stride(0), Cn, nz, ny, nx, z0, nzl, _lib.int3(perm), grid_size,
+                                 padding, p_ijk, B, C.c_void_p(out.data_ptr()), cube_stride, p_nz, p_mx,
+                                 _stream()), 'extract_cubes')
+    return out
+
+
+# ------------------------------------------------------ R7/R8 post-process + stitch
+class StitchedVolumes:
+    """The four volumes CryoEMPredictor.run_prediction returns (utils/predict.py:526-531),
+    resident on the device; ``box`` = (org, ext) of this rank's part of cube space."""
+
+    def __init__(self, cube_shape, device, org=None, ext=None):
+        self.shape = tuple(int(v) for v in cube_shape)
+        self.org = tuple(org) if org is not None else (0, 0, 0)
+        self.ext = tuple(ext) if ext is not None else self.shape
+        e = self.ext
+        self.backbone_probability = torch.zeros(e, dtype=torch.float32, device=device)
+        self.carbon_alpha_probability = torch.zeros(e, dtype=torch.float32, device=device)
+        self.amino_acid_prediction = torch.zeros(e, dtype=torch.float32, device=device)
+        self.amino_acid_probability = torch.zeros((20,) + e, dtype=torch.float32, device=device)
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k in ('backbone_probability', 'carbon_alpha_probability',
+                                              'amino_acid_prediction', 'amino_acid_probability')}
+
+
+def postproc_stitch(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: torch.Tensor,
+                    vols: StitchedVolumes, grid_size: int = 48, padding: int = 8):
+    """Fused utils/predict.py:342-349 + :494-501 for one batch of cubes."""
+    B = ijk.shape[0]
+    W = grid_size + 2 * padding
+    for t, c, name in ((bb, 4, 'bb'), (ca, 4, 'ca'), (aa, 21, 'aa')):
+        if tuple(t.shape) != (B, c, W, W, W):
+            raise _lib.MicaError(f'{name} logits must be [{B},{c},{W},{W},{W}], got {tuple(t.shape)}')
+    X, Y, Z = vols.shape
+    check(lib.mica_postproc_stitch(
+        _dev(bb, torch.float32, 'bb'), _dev(ca, torch.float32, 'ca'), _dev(aa, torch.float32, 'aa'),
+        _dev(ijk, torch.int32, 'ijk'), B, X, Y, Z, _lib.int3(vols.org), _lib.int3(vols.ext), grid_size, padding,
+        _dev(vols.backbone_probability, torch.float32, 'bb_vol'),
+        _dev(vols.carbon_alpha_probability, torch.float32, 'ca_vol'),
+        _dev(vols.amino_acid_probability, torch.float32, 'aa_prob_vol'),
+        _dev(vols.amino_acid_prediction, torch.float32, 'aa_pred_vol'), _stream()), 'postproc_stitch')
+    return vols
+
+
+def stitch_cubes(cubes: torch.Tensor, ijk: torch.Tensor, cube_shape, grid_size: int = 48, padding: int = 8,
+                 org=None, ext=None, out: torch.Tensor | None = None):
+    """reconstruct_volume alone (utils/predict.py:494-501): cubes [B,C,W,W,W] -> [C,ext...]."""
+    B, Cn = cubes.shape[:2]
+    X, Y, Z = (int(v) for v in cube_shape)
+    org = (0, 0, 0) if org is None else tuple(org)
+    ext = (X, Y, Z) if ext is None else tuple(ext)
+    if out is None:
+        out = torch.zeros((Cn,) + ext, dtype=torch.float32, device=cubes.device)
+    check(lib.mica_stitch_cubes(_dev(cubes, torch.float32, 'cubes'), Cn, _dev(ijk, torch.int32, 'ijk'), B,
+                                X, Y, Z, _lib.int3(org), _lib.int3(ext), grid_size, padding,
+                                _dev(out, torch.float32, 'out'), _stream()), 'stitch_cubes')
+    return out

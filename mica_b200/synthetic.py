@@ -1,0 +1,133 @@
+"""Seeded synthetic inputs for tests and bench.py.
+
+Not reference behaviour: the reference ships no data.  Shapes follow
+BASELINE.json ``configs``; everything derives from ``np.random.default_rng(seed)``
+(seed 2022, the reference's default ``--seed``, run.py:86).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+AMINO_ACIDS = ['ALA', 'CYS', 'ASP', 'GLU', 'PHE', 'GLY', 'HIS', 'ILE', 'LYS', 'LEU',
+               'MET', 'ASN', 'PRO', 'GLN', 'ARG', 'SER', 'THR', 'VAL', 'TRP', 'TYR']
+
+#: heavy-atom names per residue (backbone first)
+HEAVY_ATOMS = {
+    'ALA': ['N', 'CA', 'C', 'O', 'CB'],
+    'CYS': ['N', 'CA', 'C', 'O', 'CB', 'SG'],
+    'ASP': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'OD1', 'OD2'],
+    'GLU': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD', 'OE1', 'OE2'],
+    'PHE': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD1', 'CD2', 'CE1', 'CE2', 'CZ'],
+    'GLY': ['N', 'CA', 'C', 'O'],
+    'HIS': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'ND1', 'CD2', 'CE1', 'NE2'],
+    'ILE': ['N', 'CA', 'C', 'O', 'CB', 'CG1', 'CG2', 'CD1'],
+    'LYS': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD', 'CE', 'NZ'],
+    'LEU': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD1', 'CD2'],
+    'MET': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'SD', 'CE'],
+    'ASN': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'OD1', 'ND2'],
+    'PRO': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD'],
+    'GLN': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD', 'OE1', 'NE2'],
+    'ARG': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD', 'NE', 'CZ', 'NH1', 'NH2'],
+    'SER': ['N', 'CA', 'C', 'O', 'CB', 'OG'],
+    'THR': ['N', 'CA', 'C', 'O', 'CB', 'OG1', 'CG2'],
+    'VAL': ['N', 'CA', 'C', 'O', 'CB', 'CG1', 'CG2'],
+    'TRP': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD1', 'CD2', 'NE1', 'CE2', 'CE3', 'CZ2', 'CZ3', 'CH2'],
+    'TYR': ['N', 'CA', 'C', 'O', 'CB', 'CG', 'CD1', 'CD2', 'CE1', 'CE2', 'CZ', 'OH'],
+}
+
+
+def synthetic_structure(n_residues, box_xyz, seed=2022, origin_xyz=(0.0, 0.0, 0.0),
+                        margin=4.0, hetero_every=0, unknown_every=0):
+    """Random-walk C-alpha chain (3.8 A steps, reflected at the box walls) with a
+    full heavy-atom set per residue scattered within ~4 A of its C-alpha.
+
+    Returns dict(coords float32 [A,3] in (x,y,z) Angstrom, atom_names [A],
+    res_names [A], res_ids int [A], hetero bool [A]).  Coordinates are rounded to
+    3 decimals so that a PDB text round trip is exact.  ``hetero_every`` /
+    ``unknown_every`` sprinkle HETATM residues (skipped by the encoder,
+    utils/preprocessing.py:279) and non-standard residue names (no amino-acid
+    channel, :180-185) for edge-case tests."""
+    rng = np.random.default_rng(seed)
+    box = np.asarray(box_xyz, dtype=np.float64)
+    lo, hi = margin, box - margin
+    steps = rng.normal(size=(n_residues, 3))
+    steps *= 3.8 / np.linalg.norm(steps, axis=1, keepdims=True)
+    ca = np.empty((n_residues, 3))
+    pos = lo + rng.random(3) * (hi - lo)
+    for r in range(n_residues):
+        pos = pos + steps[r]
+        for a in range(3):                      # reflect at the walls
+            if pos[a] < lo:
+                pos[a] = 2 * lo - pos[a]
+            elif pos[a] > hi[a]:
+                pos[a] = 2 * hi[a] - pos[a]
+        ca[r] = pos
+    types = rng.integers(0, 20, size=n_residues)
+    coords, atom_names, res_names, res_ids, hetero = [], [], [], [], []
+    for r in range(n_residues):
+        name = AMINO_ACIDS[types[r]]
+        names = HEAVY_ATOMS[name]
+        off = rng.normal(scale=1.6, size=(len(names), 3))
+        off[names.index('CA')] = 0.0
+        xyz = ca[r] + off
+        is_het = bool(hetero_every) and (r % hetero_every == hetero_every - 1)
+        if unknown_every and (r % unknown_every == unknown_every - 1):
+            name = 'UNK'
+        coords.append(xyz)
+        atom_names += names
+        res_names += [name] * len(names)
+        res_ids += [r + 1] * len(names)
+        hetero += [is_het] * len(names)
+    coords = np.concatenate(coords) + np.asarray(origin_xyz, dtype=np.float64)
+    coords = np.round(coords, 3).astype(np.float32)
+    return dict(coords=coords, atom_names=atom_names, res_names=res_names,
+                res_ids=np.asarray(res_ids), hetero=np.asarray(hetero, dtype=bool))
+
+
+def write_pdb(path, structure):
+    """Fixed-column PDB text (one chain per 9999 residues)."""
+    with open(path, 'w') as f:
+        for n, (xyz, an, rn, rid, het) in enumerate(zip(
+                structure['coords'], structure['atom_names'], structure['res_names'],
+                structure['res_ids'], structure['hetero'])):
+            chain = chr(ord('A') + ((int(rid) - 1) // 9999) % 26)
+            rec = 'HETATM' if het else 'ATOM  '
+            aname = an if len(an) == 4 else ' ' + an
+            f.write('%s%5d %-4s %3s %s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f          %2s\n' % (
+                rec, (n + 1) % 100000, aname, rn, chain, (int(rid) - 1) % 9999 + 1,
+                xyz[0], xyz[1], xyz[2], 1.0, 0.0, an[0]))
+        f.write('END\n')
+
+
+def synthetic_map(shape_zyx, voxel=1.06, resolution=3.7, seed=2022, n_atoms=None,
+                  noise=0.05):
+    """Density-like float32 volume (z,y,x): unit point masses at random positions
+    blurred by a Gaussian of sigma = 0.225 * resolution (in Angstrom) plus
+    N(0, noise) -- positive tail, smooth, mostly background (section 8d)."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(seed)
+    shape = tuple(int(s) for s in shape_zyx)
+    nvox = int(np.prod(shape))
+    if n_atoms is None:
+        n_atoms = max(16, nvox // 400)
+    vol = np.zeros(shape, dtype=np.float32)
+    centre = np.array(shape) / 2.0
+    # atoms concentrated in a central blob (a "particle" in solvent)
+    pts = rng.normal(loc=centre, scale=np.array(shape) / 6.0, size=(n_atoms, 3))
+    pts = np.clip(np.round(pts).astype(np.int64), 0, np.array(shape) - 1)
+    np.add.at(vol, (pts[:, 0], pts[:, 1], pts[:, 2]), 1.0)
+    sigma = 0.225 * resolution / voxel
+    vol = gaussian_filter(vol, sigma=sigma, mode='constant')
+    vol /= max(float(vol.max()), 1e-12)
+    vol += rng.normal(scale=noise, size=shape).astype(np.float32)
+    return vol.astype(np.float32)
+
+
+def synthetic_logits(n_cubes, window=64, seed=2022):
+    """Stand-in model outputs [n,4,W^3], [n,4,W^3], [n,21,W^3] (float32)."""
+    rng = np.random.default_rng(seed)
+    shp = (n_cubes, window, window, window)
+    bb = rng.normal(scale=2.0, size=(n_cubes, 4) + shp[1:]).astype(np.float32)
+    ca = rng.normal(scale=2.0, size=(n_cubes, 4) + shp[1:]).astype(np.float32)
+    aa = rng.normal(scale=2.0, size=(n_cubes, 21) + shp[1:]).astype(np.float32)
+    return bb, ca, aa

@@ -1,0 +1,171 @@
+"""Executes the UNMODIFIED reference (/root/reference) in the build container.
+
+TEST INFRASTRUCTURE ONLY (see mica_oracle.py).  /root/reference does not exist
+on the GPU box, so nothing at run time may import this module; it is used by
+oracle/make_golden.py to produce tests/golden/*.npz and by the container-only
+tests that are skipped when /root/reference is absent.
+
+The reference needs ``mrcfile`` and ``Bio.PDB`` (absent from the image); the
+I/O-only stand-ins under oracle/standins/ are put on sys.path when the real
+packages cannot be imported.  No reference source is copied: the modules are
+imported from where they lie.
+"""
+from __future__ import annotations
+
+import contextlib
+import glob
+import io
+import os
+import sys
+
+import numpy as np
+
+REFERENCE_ROOT = os.environ.get('MICA_REFERENCE_ROOT', '/root/reference')
+_STANDINS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'standins')
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'utils', 'preprocessing.py'))
+
+
+def _setup_path():
+    try:
+        import mrcfile  # noqa: F401
+        import Bio.PDB  # noqa: F401
+    except ImportError:
+        if _STANDINS not in sys.path:
+            sys.path.insert(0, _STANDINS)
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+
+
+@contextlib.contextmanager
+def _quiet():
+    with contextlib.redirect_stdout(io.StringIO()):
+        yield
+
+
+def _write_mrc(path, data, voxel_xyz=(1.0, 1.0, 1.0), origin_xyz=(0, 0, 0),
+               nstart_xyz=(0, 0, 0), axes=(1, 2, 3)):
+    _setup_path()
+    import mrcfile
+    with mrcfile.new(path, overwrite=True) as m:
+        m.set_data(np.asarray(data, dtype=np.float32))
+        m.voxel_size = tuple(voxel_xyz)
+        m.header.origin.x, m.header.origin.y, m.header.origin.z = origin_xyz
+        m.header.nxstart, m.header.nystart, m.header.nzstart = nstart_xyz
+        m.header.mapc, m.header.mapr, m.header.maps = axes
+        m.update_header_stats()
+
+
+def _read_mrc(path):
+    _setup_path()
+    import mrcfile
+    with mrcfile.open(path) as m:
+        return np.array(m.data, dtype=np.float32)
+
+
+def resample_and_normalize(src, voxel_xyz, workdir, origin_xyz=(0, 0, 0),
+                           nstart_xyz=(0, 0, 0), axes=(1, 2, 3)):
+    """DataPreprocessor.resample_and_normalize_map (utils/preprocessing.py:80).
+    Returns (normalised volume or None, path of the written MRC or None)."""
+    _setup_path()
+    from utils.preprocessing import DataPreprocessor
+    map_path = os.path.join(workdir, 'input_map.mrc')
+    af3_dir = os.path.join(workdir, 'AF3_results', 'x')
+    os.makedirs(af3_dir, exist_ok=True)
+    _write_mrc(map_path, src, voxel_xyz, origin_xyz, nstart_xyz, axes)
+    with _quiet():
+        dp = DataPreprocessor(map_path=map_path, AF3_results=af3_dir + '/', quiet=True)
+        dp.logger.disabled = True
+        dp.resample_and_normalize_map()
+    out = dp.normalized_map_path
+    if out is None or not os.path.exists(out):
+        return None, None, dp
+    return _read_mrc(out), out, dp
+
+
+def af3_encodings(dp, pdb_path):
+    """DataPreprocessor.create_AF3_encodings (utils/preprocessing.py:225) on the
+    preprocessor returned by resample_and_normalize.  Returns (ok, [24,nz,ny,nx] or None)."""
+    _setup_path()
+    from mica_b200.pdb import CHANNEL_NAMES
+    with _quiet():
+        ok = dp.create_AF3_encodings(pdb_path)
+    if not ok:
+        return False, None
+    vols = [_read_mrc(os.path.join(dp.AF3_encodings, f'{n}_encoding.mrc')) for n in CHANNEL_NAMES]
+    return True, np.stack(vols)
+
+
+def grids_from_mrc(mrc_path, outdir, grid_size=48, padding=8, prefix='grid'):
+    """GridCreator.create_grids_from_mrc (utils/create_grids.py:89).  Returns
+    (grid_count, offset, {(i,j,k): (cube, di, dj, dk)}, orig_shape)."""
+    _setup_path()
+    from utils.create_grids import GridCreator
+    with _quiet():
+        gc = GridCreator(quiet=True)
+        gc.logger.disabled = True
+        count, offset = gc.create_grids_from_mrc(mrc_path, outdir, grid_size, padding, prefix)
+    cubes, orig_shape = {}, None
+    for f in sorted(glob.glob(os.path.join(outdir, f'{prefix}_i*.npz'))):
+        d = np.load(f, allow_pickle=True)
+        cubes[(int(d['i']), int(d['j']), int(d['k']))] = (
+            np.array(d['grid']), int(d['di']), int(d['dj']), int(d['dk']))
+        orig_shape = tuple(int(v) for v in d['orig_shape'])
+    return count, offset, cubes, orig_shape
+
+
+def training_grids_from_mrc(mrc_path, outdir, grid_size=48, padding=8):
+    """scripts_for_training_data/create_grids_for_normalized_map.py:18 (no
+    transpose, drops cubes whose max < 0.01)."""
+    _setup_path()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'scripts_for_training_data'))
+    import create_grids_for_normalized_map as m
+    count = m.create_and_save_grids(mrc_path, outdir, grid_size, padding)
+    cubes = {}
+    for f in sorted(glob.glob(os.path.join(outdir, 'grid_i*.npz'))):
+        d = np.load(f, allow_pickle=True)
+        cubes[(int(d['i']), int(d['j']), int(d['k']))] = (
+            np.array(d['grid']), int(d['di']), int(d['dj']), int(d['dk']))
+    return count, cubes
+
+
+class _ReplayModel:
+    """Stands where MICA stands in run_inference (utils/predict.py:339): returns
+    pre-generated logits for the cubes of the batch, keyed by the map cube's
+    content hash so that the DataLoader order does not matter."""
+
+    def __init__(self, table):
+        self.table = table
+
+    def eval(self):
+        return self
+
+    def __call__(self, x, af3):
+        import torch
+        rows = [self.table[x[b].numpy().tobytes()] for b in range(x.shape[0])]
+        self.last_af3 = af3
+        return tuple(torch.from_numpy(np.stack([r[t] for r in rows])) for t in range(3))
+
+
+def predict_and_stitch(grids_path, output_path, logits_for_cube, batch_threshold=None):
+    """CryoEMPredictor.{select_processing_strategy, prepare_data, run_inference,
+    reconstruct_and_save_volumes} (utils/predict.py:176-587) on CPU with the
+    model replaced by a logits replay.  ``logits_for_cube``: dict map-cube-bytes
+    -> (bb[4,W,W,W], ca[4,...], aa[21,...]).  Returns (ok, volumes dict)."""
+    _setup_path()
+    from utils.predict import CryoEMPredictor
+    with _quiet():
+        pr = CryoEMPredictor(model_path='unused', grids_path=grids_path.rstrip('/') + '/',
+                             output_path=output_path, save_output=False, device='cpu', quiet=True)
+        pr.logger.disabled = True
+        if batch_threshold is not None:
+            pr.batch_threshold = batch_threshold
+        assert pr.select_processing_strategy()
+        pr.model = _ReplayModel(logits_for_cube)
+        ok, loader = pr.prepare_data()
+        assert ok
+        assert pr.run_inference(loader)
+        ok, vols = pr.reconstruct_and_save_volumes()
+    return ok, vols

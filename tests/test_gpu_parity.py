@@ -1,0 +1,307 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors the unmodified reference produced (tests/golden, oracle/make_golden.py).
+
+Bars (BASELINE.json north_star): cube indexing, AF3 occupancy and the
+median / percentile thresholds bit-exact; resampled and stitched float volumes
+within 1e-5 max-abs on the [0,1] scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mica_b200 import ops, synthetic
+from oracle import mica_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def dev(a, cuda, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(cuda)
+
+
+# ------------------------------------------------------------------ R1 resample
+@pytest.mark.parametrize('shape,voxel', [
+    ((20, 23, 17), (1.06, 1.06, 1.06)),
+    ((26, 30, 22), (0.97, 1.13, 1.06)),      # anisotropic (D9): zoom list [vx,vy,vz] hits axes z,y,x
+    ((30, 30, 30), (0.83, 0.83, 0.83)),      # down-sampling
+    ((30, 36, 33), (1.2, 1.2, 1.2)),         # 30 -> 36 overshoots on z: SciPy zero last plane (D11)
+    ((64, 48, 40), (1.37, 1.21, 1.5)),
+    ((5, 4, 3), (2.0, 2.5, 3.0)),            # tiny axes: general mirror formula
+])
+@pytest.mark.parametrize('order', [3, 1])
+def test_resample_matches_scipy(cuda, shape, voxel, order):
+    rng = np.random.default_rng(hash((shape, order)) % 2**32)
+    src = rng.normal(size=shape).astype(np.float32)
+    voxel = tuple(np.float32(v) for v in voxel)
+    want = orc.resample(src, voxel, order=order)
+    zf = orc.zoom_factors(voxel)
+    out_shape = ops.zoom_output_shape(shape, zf)
+    assert out_shape == want.shape == orc.zoom_output_shape(shape, zf)
+    got = ops.resample(dev(src, cuda), out_shape, order=order).cpu().numpy()
+    scale = float(np.abs(want).max())
+    assert np.abs(got - want).max() <= 2e-6 * scale
+
+
+def test_resample_golden_then_normalize_end_to_end(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
+    src, voxel = g['src'], g['voxel']
+    zf = orc.zoom_factors(voxel)
+    res = ops.resample(dev(src, cuda), ops.zoom_output_shape(src.shape, zf))
+    assert np.abs(res.cpu().numpy() - g['oracle_resampled']).max() <= 2e-6 * np.abs(g['oracle_resampled']).max()
+    norm, st = ops.normalize(res)
+    med, p, npos, status = st.result()
+    assert status == 0
+    # end to end (resample -> stats -> clip): float tolerance on the [0,1] scale
+    assert np.abs(norm.cpu().numpy() - g['ref_normalized']).max() <= TOL
+    assert abs(float(med) - float(g['median'])) <= 1e-6 and abs(float(p) - float(g['p999'])) <= 1e-5
+
+
+# ------------------------------------------------------------- R2/R3 normalise
+def _check_normalize(x, cuda):
+    want, med, p = orc.normalize(x.copy())
+    norm, st = ops.normalize(dev(x, cuda))
+    g_med, g_p, g_npos, status = st.result()
+    if want is None:
+        assert status != 0
+        return
+    assert status == 0
+    assert g_med == np.float32(med), (g_med, med)              # bit-exact thresholds
+    assert g_p == np.float32(p), (g_p, p)
+    got = norm.cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))   # bit-exact volume
+    r_med, r_p, r_npos = orc.order_stats_restated(x)
+    assert g_npos == r_npos
+
+
+@pytest.mark.parametrize('n', [1, 2, 3, 1000, 1001, 4099, 250_000, 1_000_003])
+def test_normalize_bit_exact_sizes(cuda, n):
+    rng = np.random.default_rng(n)
+    x = (rng.normal(size=n) ** 3).astype(np.float32)
+    _check_normalize(x.reshape(-1, 1, 1) if n < 8 else x, cuda)
+
+
+def test_normalize_bit_exact_on_oracle_resampled(cuda, golden_dir):
+    """Stage isolation: feed SciPy's own float32 volume to the GPU normaliser."""
+    g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
+    norm, st = ops.normalize(dev(g['oracle_resampled'], cuda))
+    med, p, _, status = st.result()
+    assert status == 0 and med == g['median'] and p == g['p999']
+    assert np.array_equal(norm.cpu().numpy().view(np.uint32), g['ref_normalized'].view(np.uint32))
+
+
+def test_normalize_heavy_ties_and_specials(cuda):
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(40, 50, 60)).astype(np.float32)
+    x[:20] = 0.25                                   # half the volume is one constant
+    x[20:25] = np.round(x[20:25], 1)                # few distinct values
+    x[30, 0, :5] = [np.nan, np.inf, -np.inf, -0.0, 0.0]
+    _check_normalize(x, cuda)
+    y = np.zeros((16, 16, 16), np.float32)          # no positives -> failure status
+    _check_normalize(y, cuda)
+    y[3, 3, 3] = 1.0                                # a single positive
+    _check_normalize(y, cuda)
+    z = np.abs(rng.normal(size=300_001)).astype(np.float32) * 1e-42   # denormals
+    _check_normalize(z, cuda)
+    w = -np.abs(rng.normal(size=(31, 33, 35))).astype(np.float32)     # all negative
+    _check_normalize(w, cuda)
+
+
+def test_normalize_synthetic_map(cuda):
+    vol = synthetic.synthetic_map((96, 80, 72), seed=4)
+    _check_normalize(vol, cuda)
+
+
+@pytest.mark.parametrize('n', [(1 << 24) + 12345, 40_000_000])
+def test_normalize_large_float32_index_quirk(cuda, n):
+    """N > 2^24: NumPy 2 computes the percentile's virtual index in float32 (D3)."""
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(n, dtype=np.float32)
+    _check_normalize(x, cuda)
+
+
+# ---------------------------------------------------------------- R4 AF3 encode
+def _encode(st, origin, shape, cuda, keep=None):
+    keep = ~st['hetero'] if keep is None else keep
+    bb, aa = orc.channel_codes([a for a, k in zip(st['atom_names'], keep) if k],
+                               [r for r, k in zip(st['res_names'], keep) if k])
+    coords = st['coords'][keep]
+    want, ok = orc.af3_encode(coords, bb, aa, origin, shape)
+    vol, status = ops.af3_encode(dev(coords, cuda), dev(bb, cuda), dev(aa, cuda), origin, shape)
+    return want, ok, vol.cpu().numpy(), int(status.item())
+
+
+def test_af3_encode_golden(cuda, golden_dir):
+    for name in ('af3_cubic.npz',):
+        g = np.load(os.path.join(golden_dir, name))
+        shape = tuple(int(v) for v in g['shape'])
+        vol, status = ops.af3_encode(dev(g['coords'], cuda), dev(g['bb_ch'], cuda), dev(g['aa_ch'], cuda),
+                                     g['origin'], shape)
+        assert int(status.item()) == 0
+        nzi = np.argwhere(vol.cpu().numpy() > 0).astype(np.int32)
+        assert np.array_equal(nzi, g['af3_nonzero'])
+        assert set(np.unique(vol.cpu().numpy())) <= {0.0, 1.0}
+    g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))     # non-cubic: IndexError path
+    shape = g['ref_normalized'].shape
+    _, status = ops.af3_encode(dev(g['coords'], cuda), dev(g['bb_ch'], cuda), dev(g['aa_ch'], cuda),
+                               g['origin'], shape)
+    assert bool(g['af3_ok']) == (int(status.item()) == 0)
+
+
+@pytest.mark.parametrize('shape', [(40, 40, 40), (64, 48, 32), (32, 48, 64), (50, 100, 70)])
+def test_af3_encode_vs_oracle(cuda, shape):
+    nz, ny, nx = shape
+    origin = (np.float32(-12.5), np.float32(3.25), np.float32(100.0))
+    st = synthetic.synthetic_structure(300, (nx, ny, nz), seed=nz, origin_xyz=origin, margin=0.0,
+                                       hetero_every=11, unknown_every=6)
+    st['coords'][::7] += np.float32(5.0)
+    st['coords'][3::23] = np.floor(st['coords'][3::23]) + np.float32(0.5)       # ties -> half-even
+    want, ok, got, status = _encode(st, origin, shape, cuda)
+    assert ok == (status == 0)
+    if ok:
+        assert np.array_equal(got, want)
+
+
+def test_af3_encode_misclamp_quirk(cuda):
+    """D7 on (nz,ny,nx)=(70,100,50): x is clamped to nz-1=69 >= nx -> IndexError path;
+    on (50,100,70) a valid x=65 is silently moved to 49."""
+    origin = (np.float32(0), np.float32(0), np.float32(0))
+    coords = np.array([[65.2, 10.0, 20.0]], np.float32)
+    bb = np.array([0], np.int8)
+    aa = np.array([4], np.int8)
+    want, ok = orc.af3_encode(coords, bb, aa, origin, (50, 100, 70))
+    vol, status = ops.af3_encode(dev(coords, cuda), dev(bb, cuda), dev(aa, cuda), origin, (50, 100, 70))
+    assert ok and int(status.item()) == 0 and np.array_equal(vol.cpu().numpy(), want)
+    assert want[0, 20, 10, 49] == 1.0
+    want, ok = orc.af3_encode(coords, bb, aa, origin, (70, 100, 50))
+    _, status = ops.af3_encode(dev(coords, cuda), dev(bb, cuda), dev(aa, cuda), origin, (70, 100, 50))
+    assert (not ok) and int(status.item()) == 1
+
+
+def test_af3_encode_empty(cuda):
+    e = torch.zeros((0, 3), dtype=torch.float32, device=cuda)
+    c = torch.zeros((0,), dtype=torch.int8, device=cuda)
+    vol, status = ops.af3_encode(e, c, c, (0, 0, 0), (8, 9, 10))
+    assert vol.shape == (24, 8, 9, 10) and float(vol.abs().sum()) == 0 and int(status.item()) == 0
+
+
+# ------------------------------------------------------------ R5/R6 cube extract
+def _extract(vol, cuda, grid_size, padding, axes=(1, 2, 3), transpose=True):
+    if transpose:
+        perm, _ = orc.transpose_order(*axes, (0, 0, 0))
+    else:
+        perm = (0, 1, 2)
+    want, meta, shp, _ = orc.extract_cubes(vol, *axes, (0, 0, 0), grid_size, padding, transpose=transpose)
+    ijk = ops.cube_origins(ops.cube_space_shape(vol.shape, perm), grid_size)
+    assert np.array_equal(ijk, meta[:, :3])
+    got = ops.extract_cubes(dev(vol, cuda), dev(ijk, cuda), grid_size, padding, perm)
+    return want, got[:, 0].cpu().numpy()
+
+
+@pytest.mark.parametrize('axes', [(1, 2, 3), (2, 3, 1), (3, 1, 2), (1, 3, 2), (2, 1, 3), (3, 2, 1)])
+def test_extract_all_axis_orders_small_window(cuda, axes):
+    rng = np.random.default_rng(sum(axes))
+    vol = rng.random((9, 21, 13), dtype=np.float32)
+    want, got = _extract(vol, cuda, 8, 2, axes)
+    assert np.array_equal(got, want)
+
+
+def test_extract_reference_defaults_noncubic(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'cubes.npz'))
+    rng = np.random.default_rng(2022)
+    vol = rng.random((50, 100, 70), dtype=np.float32)           # same draw as make_golden
+    want, got = _extract(vol, cuda, 48, 8)
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.array([np.bitwise_xor.reduce(c.view(np.uint32).ravel()) for c in got]), g['d_xor'])
+    assert np.allclose([c.astype(np.float64).sum() for c in got], g['d_sum'], rtol=0, atol=0)
+    # dense small-window goldens incl. a non-standard axis order
+    small = g['s_vol']
+    _, got = _extract(small, cuda, 8, 2)
+    assert np.array_equal(got, g['s_cubes'])
+    _, got = _extract(small, cuda, 8, 2, axes=(2, 3, 1))
+    assert np.array_equal(got, g['a_cubes'])
+
+
+def test_extract_training_twin_no_transpose_and_max_filter(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'cubes.npz'))
+    vol = g['t_vol']
+    want, meta, _, _ = orc.extract_cubes(vol, grid_size=8, padding=2, transpose=False)
+    ijk = ops.cube_origins(vol.shape, 8)
+    cmax = torch.empty(len(ijk), dtype=torch.float32, device=cuda)
+    got = ops.extract_cubes(dev(vol, cuda), dev(ijk, cuda), 8, 2, (0, 1, 2), cube_max=cmax)
+    assert np.array_equal(got[:, 0].cpu().numpy(), want)
+    keep = cmax.cpu().numpy() >= 0.01          # create_grids_for_normalized_map.py:78
+    assert np.array_equal(ijk[keep], g['t_meta'][:, :3])
+
+
+def test_extract_stride32_multichannel_and_flags(cuda):
+    rng = np.random.default_rng(8)
+    vol = (rng.random((25, 40, 70, 50)) < 0.002).astype(np.float32)    # 25 channels, sparse
+    vol[0] = rng.random((40, 70, 50), dtype=np.float32)
+    ijk = ops.cube_origins((50, 70, 40), 32)
+    out = torch.empty((len(ijk), 25, 64, 64, 64), dtype=torch.float32, device=cuda)
+    nzf = torch.empty(len(ijk), dtype=torch.int32, device=cuda)
+    d = dev(vol, cuda)
+    ops.extract_cubes(d[:1], dev(ijk, cuda), 32, 16, out=out[:, :1])
+    ops.extract_cubes(d[1:], dev(ijk, cuda), 32, 16, out=out[:, 1:], nonzero=nzf)
+    got = out.cpu().numpy()
+    for c in (0, 1, 7, 24):
+        want, _, _, _ = orc.extract_cubes(vol[c], grid_size=32, padding=16)
+        assert np.array_equal(got[:, c], want)
+    assert np.array_equal(nzf.cpu().numpy() != 0, (np.abs(got[:, 1:]).reshape(len(ijk), -1).sum(1) > 0))
+
+
+# ------------------------------------------------------ R7/R8 post-process + stitch
+def _stitch_case(cube_shape, grid_size, padding, cuda, seed=3):
+    ijk = ops.cube_origins(cube_shape, grid_size)
+    n, W = len(ijk), grid_size + 2 * padding
+    bb, ca, aa = synthetic.synthetic_logits(n, W, seed=seed)
+    meta = np.concatenate([ijk, np.minimum(grid_size, np.array(cube_shape)[None] - ijk)], axis=1).astype(np.int64)
+    want = orc.postprocess_and_stitch(bb, ca, aa, meta, cube_shape, padding)
+    vols = ops.StitchedVolumes(cube_shape, cuda)
+    ops.postproc_stitch(dev(bb, cuda), dev(ca, cuda), dev(aa, cuda), dev(ijk, cuda), vols, grid_size, padding)
+    return want, {k: v.cpu().numpy() for k, v in vols.as_dict().items()}, (bb, ca, aa, meta)
+
+
+def _check_stitched(want, got, logits):
+    for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+        assert got[k].shape == want[k].shape and got[k].dtype == np.float32
+        assert np.abs(got[k] - want[k]).max() <= TOL, k
+    # argmax: identical wherever the oracle's top-2 probabilities are separated by more than float noise
+    p = np.sort(want['amino_acid_probability'], axis=0)
+    gap = p[-1] - p[-2]
+    diff = got['amino_acid_prediction'] != want['amino_acid_prediction']
+    assert not (diff & (gap > 4e-6)).any()
+    assert diff.mean() < 1e-4
+
+
+@pytest.mark.parametrize('cube_shape,gs,pad', [((52, 20, 12), 48, 8), ((70, 33, 50), 32, 16), ((21, 13, 9), 8, 2)])
+def test_postproc_stitch_vs_oracle(cuda, cube_shape, gs, pad):
+    want, got, logits = _stitch_case(cube_shape, gs, pad, cuda)
+    _check_stitched(want, got, logits)
+
+
+def test_postproc_stitch_golden(cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, 'stitch.npz'))
+    cube_shape = tuple(int(v) for v in g['orig_shape'])
+    want, got, _ = _stitch_case(cube_shape, 48, 8, cuda, seed=int(g['logits_seed']))
+    ref = {k: g[k] for k in want}
+    for k in want:
+        assert np.array_equal(want[k], ref[k])        # oracle == unmodified reference
+    _check_stitched(ref, got, None)
+
+
+def test_stitch_cubes_plain_paste_and_roundtrip(cuda):
+    """extract -> stitch is the identity on the volume (size-independent property)."""
+    rng = np.random.default_rng(12)
+    vol = rng.random((3, 60, 50, 70), dtype=np.float32)          # (C, nz, ny, nx)
+    cube_shape = (70, 50, 60)
+    ijk = dev(ops.cube_origins(cube_shape, 48), cuda)
+    cubes = ops.extract_cubes(dev(vol, cuda), ijk, 48, 8)
+    back = ops.stitch_cubes(cubes, ijk, cube_shape, 48, 8).cpu().numpy()
+    assert np.array_equal(back, vol.transpose(0, 3, 2, 1))
