@@ -1,0 +1,359 @@
+#!/usr/bin/env python3
+"""bench.py -- GVox/s of the map -> cubes -> stitched-volume hot path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step = one pass of the whole hot path over one synthetic map: B-spline resample to
+the 1 A grid, exact median/p99.9 normalisation, 24-channel AF3 rasterisation, 64^3 cube
+extraction into the model's input batch, and softmax/argmax + stitching of the model's
+logits into the four output volumes.  The model itself (models/model.py, PyTorch
+convolutions) is out of scope per north_star and is replaced by a ring of pre-generated
+logits larger than L2, so every byte the post-processing reads comes from HBM.
+
+N = 1 workload: BASELINE.json configs[1] -- synthetic 400^3 map at 1.2 A -> 480^3 working
+grid, 64^3 cubes at stride 32 (grid_size=32, padding=16), ~158 k atoms.
+N > 1: the same per-GPU slab (weak scaling): a (400 N) x 400 x 400 map z-slab partitioned
+over N ranks, source-halo exchange and histogram all-reduce over NCCL.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference's
+NumPy/SciPy/torch-CPU arithmetic, in memory) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'map_to_stitched_volume_throughput'
+UNIT = 'GVox/s'
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--src-edge', type=int, default=400)
+    ap.add_argument('--voxel', type=float, default=1.2)
+    ap.add_argument('--grid-size', type=int, default=32)
+    ap.add_argument('--padding', type=int, default=16)
+    ap.add_argument('--batch-cubes', type=int, default=32)
+    ap.add_argument('--cpu-edge', type=int, default=0, help='source edge of the CPU sample (0 = auto)')
+    ap.add_argument('--e2e-steps', type=int, default=2)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def algorithmic_bytes(n_src, n_vox, n_atoms, f):
+    """B(N) = 4 Ns + N (420 + 100 f) (+16 per atom)."""
+    return {
+        'resample': 4 * n_src + 4 * n_vox,
+        'normalize': 12 * n_vox,
+        'af3_encode': 96 * n_vox + 16 * n_atoms,
+        'extract': 100 * n_vox * (1 + f),
+        'postproc_stitch': 208 * n_vox,
+    }
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_sample_edge(args):
+    if args.cpu_edge:
+        return args.cpu_edge
+    runs = args.steps + args.warmup if args.impl == 'reference' else 1
+    return 100 if runs <= 4 else (80 if runs <= 12 else 64)
+
+
+def cpu_workload(edge, args):
+    from mica_b200 import synthetic
+    from oracle import mica_oracle as orc
+    src = synthetic.synthetic_map((edge,) * 3, voxel=args.voxel, seed=2022)
+    voxel = (np.float32(args.voxel),) * 3
+    n_out = orc.zoom_output_shape(src.shape, orc.zoom_factors(voxel))
+    st = synthetic.synthetic_structure(max(50, int(np.prod(n_out)) // 5500), n_out[::-1], seed=2022)
+    bb_ch, aa_ch = orc.channel_codes(st['atom_names'], st['res_names'])
+    n_cubes = int(np.prod([-(-n // args.grid_size) for n in n_out]))
+    logits = synthetic.synthetic_logits(n_cubes, args.grid_size + 2 * args.padding, seed=2022)
+    return dict(src=src, voxel=voxel, coords=st['coords'], bb_ch=bb_ch, aa_ch=aa_ch, logits=logits,
+                n_out=n_out, n_cubes=n_cubes)
+
+
+def cpu_step(w, args):
+    """The reference's arithmetic for the whole path, in memory (no .mrc/.npz I/O)."""
+    from oracle import mica_oracle as orc
+    t0 = time.perf_counter()
+    norm, af3, cubes, af3_cubes, meta, shp, off = orc.pipeline_front(
+        w['src'], w['voxel'], w['coords'], w['bb_ch'], w['aa_ch'], (0.0, 0.0, 0.0),
+        args.grid_size, args.padding)
+    vols = orc.postprocess_and_stitch(*w['logits'], meta, shp, args.padding)
+    dt = time.perf_counter() - t0
+    return dt, norm.size
+
+
+def cpu_baseline(args, steps=1, warmup=0):
+    import torch
+    edge = cpu_sample_edge(args)
+    w = cpu_workload(edge, args)
+    for _ in range(warmup):
+        cpu_step(w, args)
+    times = []
+    for _ in range(steps):
+        dt, nvox = cpu_step(w, args)
+        times.append(dt)
+    t = float(np.mean(times))
+    return {
+        'value': nvox / t / 1e9, 'unit': UNIT, 'cores': int(torch.get_num_threads()), 'kind': 'port',
+        'host_cpus': os.cpu_count(),
+        'sample': f'{edge}^3 map @ {args.voxel} A -> {"x".join(map(str, w["n_out"]))} grid, {w["n_cubes"]} cubes '
+                  f'(grid_size={args.grid_size}, padding={args.padding}), {len(w["coords"])} atoms; oracle '
+                  f'(scipy zoom + numpy + torch-CPU softmax) in memory, no file I/O; {t:.2f} s/step',
+    }, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, t = cpu_baseline(args, steps=args.steps, warmup=args.warmup)
+    f = ((args.grid_size + 2 * args.padding) / args.grid_size) ** 3
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': t * 1e3, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args, 1) | {'sampled': cb['sample']},
+        'cpu_baseline': cb,
+        'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def workload_config(args, n_gpus):
+    e = args.src_edge
+    return {
+        'workload': f'BASELINE configs[1]: synthetic {e}^3 map @ {args.voxel} A -> 1 A grid, 64^3 cubes at stride '
+                    f'{args.grid_size} (grid_size={args.grid_size}, padding={args.padding})'
+                    + (f'; weak scaling: ({e}x{n_gpus})x{e}x{e} map z-slab partitioned over {n_gpus} GPUs'
+                       if n_gpus > 1 else ''),
+        'resample': 'cubic B-spline (scipy.ndimage.zoom order=3 semantics)',
+        'model': 'excluded (north_star): logits come from a pre-generated HBM ring',
+        'batch_cubes': args.batch_cubes,
+        'l2': 'no flush needed: every stage streams buffers far larger than the 126 MB L2',
+    }
+
+
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}',
+                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.p is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        rows = [r.split(',') for r in open(self.f.name).read().strip().splitlines() if r.count(',') >= 6]
+        os.unlink(self.f.name)
+        if not rows:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        sm = [float(r[0]) for r in rows]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].strip().lower() == 'active' for r in rows)]
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(rows[0][1]), 'samples': len(rows),
+                'power_w_max': max(float(r[2]) for r in rows), 'reasons': reasons}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mica_b200 import ops, synthetic
+    from mica_b200.pdb import channel_codes
+    from mica_b200.pipeline import MapHeader, MapPipeline, StageTimer, run_map_pipeline_host
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit('launch with torch.distributed.run for --gpus > 1')
+    ops.require_gpu()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    # ---------------- synthetic inputs (host), seed 2022
+    e = args.src_edge
+    src_np = synthetic.synthetic_map((e, e, e), voxel=args.voxel, seed=2022 + rank)
+    header = MapHeader(voxel_size=(np.float32(args.voxel),) * 3)
+    n_out = ops.zoom_output_shape(src_np.shape, [np.float32(args.voxel)] * 3)
+    st = synthetic.synthetic_structure(20000, n_out[::-1], seed=2022 + rank)
+    bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
+    src_host = torch.from_numpy(src_np).pin_memory()
+    atoms_host = (torch.from_numpy(st['coords']).pin_memory(), torch.from_numpy(bb_ch).pin_memory(),
+                  torch.from_numpy(aa_ch).pin_memory())
+    src = src_host.to(dev)
+    atoms = tuple(t.to(dev) for t in atoms_host)
+
+    if world > 1:
+        from mica_b200.slab import SlabPipeline
+        pipe = SlabPipeline(dev, rank, world, grid_size=args.grid_size, padding=args.padding,
+                            batch_cubes=args.batch_cubes)
+    else:
+        pipe = MapPipeline(dev, grid_size=args.grid_size, padding=args.padding, batch_cubes=args.batch_cubes)
+
+    # ---------------- logits ring (stands where MICA.forward stands), >> L2
+    W, B = args.grid_size + 2 * args.padding, args.batch_cubes
+    gen = torch.Generator(device=dev).manual_seed(2022)
+    ring = [tuple(torch.randn((B, c, W, W, W), generator=gen, device=dev) * 2 for c in (4, 4, 21)) for _ in range(2)]
+    state = {'i': 0}
+
+    def model_fn(x, af):
+        bb, ca, aa = ring[state['i'] % len(ring)]
+        state['i'] += 1
+        b = x.shape[0]
+        return bb[:b], ca[:b], aa[:b]
+
+    vols = None
+
+    def step():
+        nonlocal vols
+        vols = pipe.run(src, header, atoms, model_fn, vols)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    timer = StageTimer()
+    pipe.timer = timer
+    launches0 = ops.launch_count()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    launches = ops.launch_count() - launches0
+    clk = clocks.stop() if clocks else None
+    stages = timer.summary()
+    pipe.timer = __import__('mica_b200.pipeline', fromlist=['_no_timer'])._no_timer
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_vox_rank = int(np.prod(pipe.normalized.shape)) if world == 1 else pipe.owned_voxels
+    n_vox = n_vox_rank * world
+    ms_per_step = ms / args.steps
+    value = n_vox / (ms_per_step * 1e-3) / 1e9
+
+    # ---------------- end to end through the public API with host buffers
+    e2e = None
+    if world == 1:
+        out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in vols.as_dict().items()}
+        run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)       # warm
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _, h2d, d2h = run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        e2e = {'value': n_vox / dt / 1e9, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
+               'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
+               'note': 'pinned host map + atoms -> device -> four stitched volumes -> pinned host'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (AF3-channel cube extract)
+    peak, peak_src = peaks()
+    S = args.grid_size
+    f = (W / S) ** 3
+    n_src = src.numel()
+    n_atoms = atoms[0].shape[0]
+    alg = algorithmic_bytes(n_src, n_vox_rank, n_atoms, f)
+    calls, tot_ms = stages.get('extract_af3', (0, 0.0))
+    n_cubes = len(pipe.ijk_host)
+    per_launch_bytes = 24 * 4 * (S ** 3 + W ** 3) * (n_cubes / max(1, calls / args.steps))
+    dur_ms = tot_ms / max(1, calls)
+    achieved = per_launch_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms else 0.0
+    stage_ms = {k: round(v[1] / args.steps, 4) for k, v in stages.items()}
+    stage_frac = {}
+    for name, keys in (('resample', ['resample']), ('normalize', ['order_stats', 'normalize_apply']),
+                       ('af3_encode', ['af3_encode']), ('extract', ['extract_map', 'extract_af3']),
+                       ('postproc_stitch', ['postproc_stitch'])):
+        t_ms = sum(stage_ms.get(k, 0.0) for k in keys)
+        if t_ms:
+            stage_frac[name] = round(alg[name] / (t_ms * 1e-3) / 1e9 / peak, 4)
+    total_alg = sum(alg.values())
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f32', 'data': 'synthetic (seed 2022; random-init stand-in logits)',
+        'config': workload_config(args, world) | {'working_grid': list(pipe.normalized.shape), 'cubes': n_cubes,
+                                                   'atoms': int(n_atoms)},
+        'roofline': {
+            'bound': 'hbm', 'kernel': 'extract_transpose_kernel<0> (24 AF3 channels per cube batch)',
+            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+            'peak_source': peak_src, 'launch_ms': dur_ms, 'algorithmic_bytes_per_launch': per_launch_bytes,
+            'whole_path': {'algorithmic_bytes_per_voxel': total_alg / n_vox_rank,
+                           'achieved': total_alg / (ms_per_step * 1e-3) / 1e9,
+                           'frac': total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+            'stage_ms_per_step': stage_ms, 'stage_frac_of_peak': stage_frac,
+        },
+        'clocks': clk, 'gpu_launches': int(launches), 'e2e': e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line['cpu_baseline'], _ = cpu_baseline(args)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

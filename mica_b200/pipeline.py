@@ -1,0 +1,253 @@
+"""The voxel-parallel map pipeline, resident in HBM end to end.
+
+    source map --resample--> 1 A grid --median/p99.9--> normalised map ---+
+    docked atoms --rasterise--> 24-channel AF3 volume --------------------+--> 64^3 cube batches
+        --> [model: models/model.py MICA, unchanged PyTorch] --> logits --softmax/argmax+stitch--> 4 volumes
+
+This is the dataflow of Solver.getData + Solver.nnPred (utils/modeler.py:673-760 in the
+reference) with every .mrc / .npz round trip removed: the stages hand device tensors to
+each other and the cubes are cut straight into the model's input batch.  The reference
+entry points (DataPreprocessor / GridCreator / CryoEMPredictor mirrors in
+preprocessing.py, create_grids.py, predict.py) are thin shells over this class.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from ._lib import MicaError, NORM_OK
+
+
+@dataclass
+class MapHeader:
+    """The MRC header fields the reference carries through (utils/preprocessing.py:99-107)."""
+    voxel_size: tuple = (1.0, 1.0, 1.0)       # (x, y, z)
+    origin: tuple = (0.0, 0.0, 0.0)           # (x, y, z)
+    mapc: int = 1
+    mapr: int = 2
+    maps: int = 3
+    nxstart: int = 0
+    nystart: int = 0
+    nzstart: int = 0
+
+    def transpose_order(self):
+        """GridCreator.transpose bookkeeping (utils/create_grids.py:67-87,120-122):
+        returns (perm, offset) with perm[m] = memory axis walked by cube axis m."""
+        axis_order = [int(self.maps) - 1, int(self.mapr) - 1, int(self.mapc) - 1]
+        start = [float(self.nzstart), float(self.nystart), float(self.nxstart)]
+        perm, offset = [], []
+        for i in range(3):
+            for j in range(3):
+                if axis_order[j] == i:
+                    offset.append(start[j])
+                    perm.append(j)
+        return tuple(perm), offset
+
+
+def zoom_factors(voxel_size_xyz, target_voxel_size=1.0):
+    """[vx, vy, vz] / target, float32 as under NumPy 2, applied to axes (z,y,x) in that
+    order -- the reference's own (anisotropy-swapping) convention, utils/preprocessing.py:112-117."""
+    return [np.float32(v) / target_voxel_size for v in voxel_size_xyz]
+
+
+class StageTimer:
+    """CUDA-event timing of the pipeline's stages on the launching stream.  Events are
+    recorded around every stage call; ``summary()`` (after a synchronize) returns
+    {stage: (calls, total_ms)}."""
+
+    def __init__(self):
+        self.spans = []
+
+    @contextmanager
+    def __call__(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        try:
+            yield
+        finally:
+            b.record()
+            self.spans.append((name, a, b))
+
+    def summary(self):
+        out = {}
+        for name, a, b in self.spans:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + a.elapsed_time(b))
+        return out
+
+    def reset(self):
+        self.spans = []
+
+
+@contextmanager
+def _no_timer(name):
+    yield
+
+
+class MapPipeline:
+    """One GPU's share of the hot path.  With ``slab`` left None it owns the whole map."""
+
+    def __init__(self, device, grid_size: int = 48, padding: int = 8, order: int = 3,
+                 batch_cubes: int = 16, target_voxel_size: float = 1.0):
+        ops.require_gpu()
+        self.device = torch.device(device)
+        self.grid_size, self.padding, self.order = int(grid_size), int(padding), int(order)
+        self.window = self.grid_size + 2 * self.padding
+        self.batch_cubes = int(batch_cubes)
+        self.target_voxel_size = target_voxel_size
+        self.header = MapHeader()
+        self.normalized = None          # [nz,ny,nx] float32, device
+        self.af3 = None                 # [24,nz,ny,nx] float32, device (None -> zero AF3 features)
+        self.stats = None
+        self.norm_status = None
+        self._x = self._af = None
+        self.timer = _no_timer      # bench.py swaps in a StageTimer
+
+    # ------------------------------------------------------------------ stage 1+2
+    def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
+        """utils/preprocessing.py:98-133 on the device.  Returns True on success; on the
+        reference's two failure modes (:152-157) returns False and leaves ``normalized`` None.
+        ``defer_status=True`` skips the host read-back (one stream sync) -- the caller then
+        calls ``check_status()`` once everything is enqueued."""
+        if header is not None:
+            self.header = header
+        zf = zoom_factors(self.header.voxel_size, self.target_voxel_size)
+        out_shape = ops.zoom_output_shape(src.shape, zf)
+        with self.timer('resample'):
+            if all(float(z) == 1.0 for z in zf):              # SciPy early exit (D10): plain copy
+                res = src.clone()
+            else:
+                res = ops.resample(src, out_shape, order=self.order)
+        with self.timer('order_stats'):
+            self.stats = ops.OrderStats(self.device).run(res)
+        with self.timer('normalize_apply'):
+            self.normalized = self.stats.apply(res, res)       # in place: the resampled map is not kept
+        self.norm_status = None
+        return True if defer_status else self.check_status()
+
+    def check_status(self):
+        med, p, npos, status = self.stats.result()
+        self.norm_status = status
+        self.median, self.p999, self.n_pos = med, p, npos
+        if status != NORM_OK:
+            self.normalized = None
+        return status == NORM_OK
+
+    def set_normalized(self, norm: torch.Tensor, header: MapHeader | None = None):
+        if header is not None:
+            self.header = header
+        self.normalized = norm
+
+    # -------------------------------------------------------------------- stage 3
+    def encode_af3(self, coords: torch.Tensor, bb_ch: torch.Tensor, aa_ch: torch.Tensor, defer_status=False):
+        """utils/preprocessing.py:268-298.  Returns True iff the reference would have
+        succeeded (no IndexError from the mis-ordered clip, D7)."""
+        if self.normalized is None:
+            raise MicaError('encode_af3 needs the normalised map (its shape and origin)')
+        with self.timer('af3_encode'):
+            vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, tuple(self.normalized.shape))
+        self.af3, self._af3_status = vol, status
+        if defer_status:
+            return True
+        ok = int(status.item()) == 0
+        self.af3 = vol if ok else None
+        return ok
+
+    # -------------------------------------------------------------------- stage 4
+    def cube_index(self):
+        perm, offset = self.header.transpose_order()
+        self.perm, self.offset = perm, offset
+        self.cube_shape = ops.cube_space_shape(self.normalized.shape, perm)
+        self.ijk_host = ops.cube_origins(self.cube_shape, self.grid_size)
+        self.ijk = torch.from_numpy(self.ijk_host).to(self.device)
+        return self.ijk_host
+
+    def _buffers(self, B):
+        W = self.window
+        if self._x is None or self._x.shape[0] < B:
+            self._x = torch.empty((B, 1, W, W, W), dtype=torch.float32, device=self.device)
+            self._af = torch.empty((B, 24, W, W, W), dtype=torch.float32, device=self.device)
+            self._nz = torch.empty(B, dtype=torch.int32, device=self.device)
+        return self._x[:B], self._af[:B], self._nz[:B]
+
+    def extract_batch(self, b0: int, b1: int, want_flags: bool = False):
+        """Cubes [b0,b1) -> (exp_map [B,1,W,W,W], af_features [B,24,W,W,W][, nonzero flags])
+        -- the two tensors MICA.forward takes (models/model.py:331)."""
+        x, af, nzf = self._buffers(b1 - b0)
+        ijk = self.ijk[b0:b1]
+        with self.timer('extract_map'):
+            ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x)
+        if self.af3 is not None:
+            with self.timer('extract_af3'):
+                ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
+                                  nonzero=nzf if want_flags else None)
+        else:
+            af.zero_()                                         # dataset/dataset.py:218-219
+            if want_flags:
+                nzf.zero_()
+        return (x, af, nzf) if want_flags else (x, af)
+
+    # ---------------------------------------------------------------- stage 5 (+model)
+    def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None):
+        """run_inference + reconstruct_volume (utils/predict.py:307-587) without the
+        per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits."""
+        if self.normalized is None:
+            raise MicaError('no normalised map')
+        self.cube_index()
+        if vols is None:
+            vols = ops.StitchedVolumes(self.cube_shape, self.device)
+        n = len(self.ijk_host)
+        for b0 in range(0, n, self.batch_cubes):
+            b1 = min(n, b0 + self.batch_cubes)
+            x, af = self.extract_batch(b0, b1)
+            bb, ca, aa = model_fn(x, af)
+            with self.timer('postproc_stitch'):
+                ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+        return vols
+
+    # ------------------------------------------------------------------ whole path
+    def run(self, src, header, atoms, model_fn, vols=None):
+        """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
+        device tensors or None.  Raises on the reference's normalisation failures."""
+        self.resample_and_normalize(src, header, defer_status=True)
+        if atoms is not None:
+            self.encode_af3(*atoms, defer_status=True)
+        else:
+            self.af3 = None
+        vols = self.predict_and_stitch(model_fn, vols)
+        # one host read-back for the whole path (the reference reports these per stage)
+        if not self.check_status():
+            raise MicaError(f'normalisation failed (status {self.norm_status})')
+        if atoms is not None and int(self._af3_status.item()) != 0:
+            raise MicaError('AF3 encoding failed: atom index outside the grid (reference IndexError path, D7)')
+        return vols
+
+
+def run_map_pipeline_host(src_host: torch.Tensor, header: MapHeader, atoms_host, model_fn, pipe: MapPipeline,
+                          out_host: dict | None = None):
+    """The call a user of the reference makes, with HOST buffers on both sides: pinned
+    source map (+ atom arrays) in, the four stitched volumes out in pinned host memory.
+    Returns (volumes dict of host tensors, h2d_bytes, d2h_bytes)."""
+    dev = pipe.device
+    src = src_host.to(dev, non_blocking=True)
+    h2d = src_host.numel() * src_host.element_size()
+    atoms = None
+    if atoms_host is not None:
+        atoms = tuple(t.to(dev, non_blocking=True) for t in atoms_host)
+        h2d += sum(t.numel() * t.element_size() for t in atoms_host)
+    vols = pipe.run(src, header, atoms, model_fn)
+    d2h = 0
+    out = {}
+    for k, v in vols.as_dict().items():
+        if out_host is not None and k in out_host:
+            out[k] = out_host[k]
+            out[k].copy_(v, non_blocking=True)
+        else:
+            out[k] = v.to('cpu', non_blocking=False)
+        d2h += v.numel() * v.element_size()
+    torch.cuda.current_stream().synchronize()
+    return out, h2d, d2h

@@ -126,8 +126,11 @@ def synthetic_map(shape_zyx, voxel=1.06, resolution=3.7, seed=2022, n_atoms=None
 def synthetic_logits(n_cubes, window=64, seed=2022):
     """Stand-in model outputs [n,4,W^3], [n,4,W^3], [n,21,W^3] (float32)."""
     rng = np.random.default_rng(seed)
-    shp = (n_cubes, window, window, window)
-    bb = rng.normal(scale=2.0, size=(n_cubes, 4) + shp[1:]).astype(np.float32)
-    ca = rng.normal(scale=2.0, size=(n_cubes, 4) + shp[1:]).astype(np.float32)
-    aa = rng.normal(scale=2.0, size=(n_cubes, 21) + shp[1:]).astype(np.float32)
-    return bb, ca, aa
+    vox = (window, window, window)
+
+    def draw(c):
+        a = rng.standard_normal((n_cubes, c) + vox, dtype=np.float32)
+        a *= np.float32(2.0)
+        return a
+
+    return draw(4), draw(4), draw(21)
