@@ -138,6 +138,10 @@ int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_channels,
                        float* out, int64_t out_cube_stride, int32_t* nonzero, float* cube_max,
                        mica_stream_t stream);
 
+/* diagnostic: which kernel the last mica_extract_cubes call on this thread used
+ * (0 = row copy, 1 = shared-memory tiled transpose, 2 = TMA box loads; -1 = none yet) */
+int mica_last_extract_path(void);
+
 /* ------------------------------------------------ R7/R8 post-process + stitch
  * Replaces the softmax/argmax block of run_inference (utils/predict.py:342-349)
  * and reconstruct_volume (utils/predict.py:439-512) in one pass over the cube

@@ -12,7 +12,10 @@
 // axis is the memory-contiguous one, so the copy is a tiled transpose through shared
 // memory (32x33 tiles: coalesced 128-byte reads along x, coalesced 128-byte writes
 // along the cube's fastest axis).  Pure index work: bit-exact.
+#include <cuda.h>
 #include <math_constants.h>
+
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -138,6 +141,112 @@ extract_transpose_kernel(ExtractParams P) {
   block_flags(P, b, any_nz, vmax);
 }
 
+
+// ---- TMA path for the standard layout (cube axis 0 is memory-contiguous, W % 32 == 0,
+// 16-byte aligned rows): one CTA = one [32 a] x [BT b] x [W c] tile of one (cube, channel).
+// A single elected thread issues ONE cp.async.bulk.tensor box load of a rank-4 tensor map
+// whose dims are ordered (x, c-axis, b-axis, channel), so the box lands in shared memory as
+// [b][c][32 x] rows of exactly 128 bytes with the 128-byte hardware swizzle; negative or
+// too-large coordinates are zero-filled by the TMA unit, which IS the reference's np.pad.
+// Consumers read float4 (4 consecutive a) along lanes = c -- conflict-free thanks to the
+// swizzle -- and issue four fully coalesced 128-byte streaming stores per warp.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+struct TmaExtractParams {
+  const int32_t* ijk;
+  float* out;
+  int64_t out_cube_stride;
+  int32_t* nonzero;
+  float* cube_max;
+  int W, pad;
+  int off_c, off_b;  // slab offsets subtracted from the tensor-map coordinates of dims 1 and 2
+};
+
+template <int BT>
+__global__ void __launch_bounds__(256)
+extract_tma_kernel(const __grid_constant__ CUtensorMap tmap, TmaExtractParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  uint8_t* tile = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int W = P.W;
+  const int a_tiles = W >> 5;
+  const int a0 = (blockIdx.x % a_tiles) << 5, b0 = (blockIdx.x / a_tiles) * BT;
+  const int ch = blockIdx.y, cube = blockIdx.z;
+  const int i0 = P.ijk[3 * cube + 0] - P.pad, j0 = P.ijk[3 * cube + 1] - P.pad, k0 = P.ijk[3 * cube + 2] - P.pad;
+  const uint32_t bar_a = smem_u32(&bar), tile_a = smem_u32(tile);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t bytes = (uint32_t)BT * W * 128u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(tile_a), "l"(&tmap), "r"(i0 + a0), "r"(k0 - P.off_c), "r"(j0 + b0 - P.off_b), "r"(ch), "r"(bar_a)
+        : "memory");
+  }
+  {  // wait for the box (phase 0)
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done) : "r"(bar_a) : "memory");
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c_groups = W >> 5;
+  const int64_t W2 = (int64_t)W * W;
+  float* dst = P.out + (int64_t)cube * P.out_cube_stride + (int64_t)ch * W2 * W + (int64_t)a0 * W2 + (int64_t)b0 * W;
+  bool any_nz = false;
+  float vmax = -CUDART_INF_F;
+  const int items = BT * c_groups * 8;
+#pragma unroll 4
+  for (int it = warp; it < items; it += 8) {
+    const int j = it & 7, cg = (it >> 3) % c_groups, y = (it >> 3) / c_groups;
+    const int z = (cg << 5) + lane;
+    const int R = y * W + z;
+    const float4 v = *reinterpret_cast<const float4*>(tile + (size_t)R * 128 + (((j ^ (R & 7))) << 4));
+    float* o = dst + (int64_t)(4 * j) * W2 + (int64_t)y * W + z;
+    st_stream(o, v.x);
+    st_stream(o + W2, v.y);
+    st_stream(o + 2 * W2, v.z);
+    st_stream(o + 3 * W2, v.w);
+    any_nz |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+    vmax = fmaxf(fmaxf(vmax, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+  }
+  if (P.nonzero) {
+    if (__syncthreads_or(any_nz) && threadIdx.x == 0) atomicOr(&P.nonzero[cube], 1);
+  }
+  if (P.cube_max && ch == 0) {
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane == 0) atomic_max_f32(&P.cube_max[cube], vmax);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+constexpr int kTmaBT = 4;  // b-rows per tile: 4 * 64 * 128 B = 32 KB of shared memory per CTA
+
 __global__ void init_flags_kernel(int32_t* nonzero, float* cube_max, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -148,6 +257,9 @@ __global__ void init_flags_kernel(int32_t* nonzero, float* cube_max, int n) {
 }  // namespace mica
 
 using namespace mica;
+
+static thread_local int g_last_extract_path = -1;
+extern "C" int mica_last_extract_path(void) { return g_last_extract_path; }
 
 extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_channels,
                                   int nz, int ny, int nx, int z0, int nz_local, const int perm[3],
@@ -191,6 +303,33 @@ extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_c
   P.cube_max = cube_max;
 
   const int contiguous_axis = perm[0] == 2 ? 0 : (perm[1] == 2 ? 1 : 2);
+
+  // TMA path: standard layout, window a multiple of 32, 16-byte aligned base / rows / channels
+  CUtensorMap tmap;
+  bool use_tma = false;
+  const size_t tma_smem = (size_t)kTmaBT * W * 128 + 1024;
+  if (contiguous_axis == 0 && W % 32 == 0 && W <= 256 && nx % 4 == 0 && chan_stride % 4 == 0 &&
+      ((uintptr_t)vol & 15) == 0 && !getenv("MICA_NO_TMA")) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (enc) {
+      const int local[3] = {nz_local, ny, nx};
+      // dims: (x, axis walked by c, axis walked by b, channel)
+      cuuint64_t gdim[4] = {(cuuint64_t)nx, (cuuint64_t)local[perm[2]], (cuuint64_t)local[perm[1]],
+                            (cuuint64_t)n_channels};
+      cuuint64_t gstr[3] = {(cuuint64_t)memstride[perm[2]] * 4, (cuuint64_t)memstride[perm[1]] * 4,
+                            (cuuint64_t)(n_channels > 1 ? chan_stride : (int64_t)nz_local * ny * nx) * 4};
+      cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)kTmaBT, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)vol, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r == CUDA_SUCCESS) {
+        use_tma = true;
+        MICA_CUDA(cudaFuncSetAttribute(extract_tma_kernel<kTmaBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)tma_smem));
+      }
+    }
+  }
   const int kMaxZ = 32768;
   for (int b0 = 0; b0 < n_cubes; b0 += kMaxZ) {
     const int nb = (n_cubes - b0 < kMaxZ) ? n_cubes - b0 : kMaxZ;
@@ -203,12 +342,26 @@ extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_c
       MICA_LAUNCH_CHECK("init_flags_kernel");
     }
     dim3 grid(W, n_channels, nb), block(32, 8);
-    if (contiguous_axis == 2)
+    if (use_tma) {
+      TmaExtractParams T;
+      T.ijk = P.ijk;
+      T.out = P.out;
+      T.out_cube_stride = out_cube_stride;
+      T.nonzero = P.nonzero;
+      T.cube_max = P.cube_max;
+      T.W = W;
+      T.pad = padding;
+      T.off_c = perm[2] == 0 ? z0 : 0;
+      T.off_b = perm[1] == 0 ? z0 : 0;
+      dim3 tgrid((W / 32) * (W / kTmaBT), n_channels, nb);
+      extract_tma_kernel<kTmaBT><<<tgrid, 256, tma_smem, st>>>(tmap, T);
+    } else if (contiguous_axis == 2)
       extract_rows_kernel<<<grid, block, 0, st>>>(P);
     else if (contiguous_axis == 0)
       extract_transpose_kernel<0><<<grid, block, 0, st>>>(P);
     else
       extract_transpose_kernel<1><<<grid, block, 0, st>>>(P);
+    g_last_extract_path = use_tma ? 2 : (contiguous_axis == 2 ? 0 : 1);
     MICA_LAUNCH_CHECK("extract_cubes kernel");
   }
   return MICA_OK;

@@ -256,6 +256,32 @@ def test_extract_stride32_multichannel_and_flags(cuda):
     assert np.array_equal(nzf.cpu().numpy() != 0, (np.abs(got[:, 1:]).reshape(len(ijk), -1).sum(1) > 0))
 
 
+@pytest.mark.parametrize('gs,pad', [(48, 8), (32, 16)])
+@pytest.mark.parametrize('shape', [(44, 52, 60), (100, 36, 64), (33, 70, 128)])
+def test_extract_tma_path_matches_oracle_and_fallback(cuda, shape, gs, pad, monkeypatch):
+    """nx % 4 == 0 and W == 64 take the TMA box-load kernel; it must equal both the oracle
+    and the shared-memory transpose kernel (forced with MICA_NO_TMA)."""
+    from mica_b200._lib import lib
+    rng = np.random.default_rng(shape[0])
+    vol = rng.normal(size=(3,) + shape).astype(np.float32)
+    vol[2] = (rng.random(shape) < 0.001)
+    ijk = ops.cube_origins(ops.cube_space_shape(shape), gs)
+    d_vol, d_ijk = dev(vol, cuda), dev(ijk, cuda)
+    nzf = torch.empty(len(ijk), dtype=torch.int32, device=cuda)
+    cmax = torch.empty(len(ijk), dtype=torch.float32, device=cuda)
+    got = ops.extract_cubes(d_vol, d_ijk, gs, pad, nonzero=nzf, cube_max=cmax).cpu().numpy()
+    assert lib.mica_last_extract_path() == 2
+    monkeypatch.setenv('MICA_NO_TMA', '1')
+    ref = ops.extract_cubes(d_vol, d_ijk, gs, pad).cpu().numpy()
+    assert lib.mica_last_extract_path() == 1
+    assert np.array_equal(got, ref)
+    for c in range(3):
+        want, _, _, _ = orc.extract_cubes(vol[c], grid_size=gs, padding=pad)
+        assert np.array_equal(got[:, c], want)
+    assert np.array_equal(nzf.cpu().numpy() != 0, np.abs(got).reshape(len(ijk), -1).sum(1) > 0)
+    assert np.array_equal(cmax.cpu().numpy(), got[:, 0].reshape(len(ijk), -1).max(1))
+
+
 # ------------------------------------------------------ R7/R8 post-process + stitch
 def _stitch_case(cube_shape, grid_size, padding, cuda, seed=3):
     ijk = ops.cube_origins(cube_shape, grid_size)
