@@ -1,0 +1,82 @@
+"""Host-side I/O of the drop-in: MRC2014 round trips against the
+independent stand-in the reference harness uses, and the fixed-column PDB reader."""
+import os
+import sys
+
+import numpy as np
+
+from mica_b200 import mrc, pdb, synthetic
+from mica_b200.pipeline import MapHeader, zoom_factors
+from oracle import mica_oracle as orc
+
+STANDINS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'standins')
+
+
+def _standin_mrcfile():
+    sys.path.insert(0, STANDINS)
+    try:
+        import importlib
+        return importlib.import_module('mrcfile')
+    finally:
+        sys.path.remove(STANDINS)
+
+
+def test_mrc_roundtrip_and_cross_read(tmp_path):
+    rng = np.random.default_rng(0)
+    data = rng.normal(size=(5, 7, 9)).astype(np.float32)
+    m = mrc.MrcMap(data=data, voxel_size=(np.float32(1.06), np.float32(1.1), np.float32(0.9)),
+                   origin=(np.float32(-3.5), np.float32(2.25), np.float32(10)), mapc=2, mapr=3, maps=1,
+                   nxstart=4, nystart=-5, nzstart=6)
+    p = str(tmp_path / 'a.mrc')
+    mrc.write_mrc(p, m)
+    r = mrc.read_mrc(p)
+    assert np.array_equal(r.data, data) and (r.mapc, r.mapr, r.maps) == (2, 3, 1)
+    assert (r.nxstart, r.nystart, r.nzstart) == (4, -5, 6)
+    assert r.origin == m.origin
+    mf = _standin_mrcfile()
+    with mf.open(p) as f:                                       # what the reference would see
+        assert np.array_equal(f.data, data)
+        assert (int(f.header.mapc), int(f.header.nzstart)) == (2, 6)
+        assert np.float32(f.voxel_size.x) == r.voxel_size[0] and np.float32(f.voxel_size.z) == r.voxel_size[2]
+        assert np.float32(f.header.origin.y) == np.float32(2.25)
+    p2 = str(tmp_path / 'b.mrc')
+    with mf.new(p2, overwrite=True) as f:                       # what the reference would write
+        f.set_data(data)
+        f.voxel_size = (1.2, 1.2, 1.2)
+        f.header.origin.x = 7
+        f.header.nystart = 3
+    r2 = mrc.read_mrc(p2)
+    assert np.array_equal(r2.data, data) and r2.voxel_size[1] == np.float32(np.float32(1.2 * 7) / np.float32(7))
+    assert r2.origin[0] == 7 and r2.nystart == 3
+
+
+def test_pdb_reader_matches_biopython_standin(tmp_path):
+    st = synthetic.synthetic_structure(50, (30, 30, 30), seed=3, hetero_every=6, unknown_every=5)
+    p = str(tmp_path / 's.pdb')
+    synthetic.write_pdb(p, st)
+    coords, bb, aa, nres = pdb.read_pdb_atoms(p)
+    keep = ~st['hetero']
+    assert np.array_equal(coords, st['coords'][keep])           # %8.3f text round trip is exact
+    obb, oaa = orc.channel_codes([a for a, k in zip(st['atom_names'], keep) if k],
+                                 [r for r, k in zip(st['res_names'], keep) if k])
+    assert np.array_equal(bb, obb) and np.array_equal(aa, oaa)
+    sys.path.insert(0, STANDINS)
+    try:
+        from Bio import PDB
+        structure = PDB.PDBParser(QUIET=True).get_structure('x', p)
+    finally:
+        sys.path.remove(STANDINS)
+    atoms = [(a.get_name(), r.get_resname(), a.get_coord()) for m in structure for c in m for r in c
+             if r.get_id()[0] == ' ' for a in r]
+    assert len(atoms) == len(coords)
+    assert np.array_equal(np.stack([a[2] for a in atoms]), coords)
+
+
+def test_header_transpose_and_zoom_bookkeeping():
+    for axes in [(1, 2, 3), (2, 3, 1), (3, 1, 2), (1, 3, 2), (2, 1, 3), (3, 2, 1)]:
+        h = MapHeader(mapc=axes[0], mapr=axes[1], maps=axes[2], nxstart=4, nystart=-7, nzstart=11)
+        perm, off = h.transpose_order()
+        operm, ooff = orc.transpose_order(*axes, (11, -7, 4))
+        assert list(perm) == list(operm) and off == ooff
+    v = (np.float32(1.06), np.float32(1.13), np.float32(0.97))
+    assert [float(a) for a in zoom_factors(v)] == [float(a) for a in orc.zoom_factors(v)]
