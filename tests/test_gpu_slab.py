@@ -1,0 +1,98 @@
+"""The z-slab partitioned path, emulated rank by rank on ONE GPU (the histogram all-reduce
+is replaced by an explicit sum between the hist and pick kernels of every rank, in
+lock-step), must reproduce the single-GPU pipeline and the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from mica_b200 import _lib, ops, synthetic
+from mica_b200.pdb import channel_codes
+from mica_b200.pipeline import MapHeader, MapPipeline
+from mica_b200.slab import SlabPipeline, SlabPlan
+from oracle import mica_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _lockstep_stats(ranks, owned, n_total):
+    """What ops.OrderStats.run(all_reduce=...) does on every rank of a real group."""
+    lib = _lib.lib
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    stats = [ops.OrderStats(o.device) for o in owned]
+    for s in stats:
+        _lib.check(lib.mica_select_init(s._p, n_total, st))
+    for _ in range(_lib.SELECT_PASSES):
+        for s, o in zip(stats, owned):
+            _lib.check(lib.mica_select_hist(C.c_void_p(o.data_ptr()), o.numel(), s._p, st))
+        total = sum(s.hist_view().clone() for s in stats)
+        for s in stats:
+            s.hist_view().copy_(total)
+            _lib.check(lib.mica_select_pick(s._p, st))
+    return stats
+
+
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('src_shape,voxel,gs,pad', [((120, 40, 36), 1.2, 32, 16), ((144, 32, 32), 1.0, 48, 8)])
+def test_emulated_slab_ranks_match_single_gpu(cuda, world, src_shape, voxel, gs, pad):
+    src = synthetic.synthetic_map(src_shape, voxel=voxel, seed=13)
+    hdr = MapHeader(voxel_size=(np.float32(voxel),) * 3)
+    d_src = torch.from_numpy(src).to(cuda)
+    single = MapPipeline(cuda, gs, pad, batch_cubes=4)
+    assert single.resample_and_normalize(d_src, hdr)
+    n_out = tuple(single.normalized.shape)
+    st = synthetic.synthetic_structure(150, n_out[::-1], seed=13)
+    bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
+    atoms = tuple(torch.from_numpy(a).to(cuda) for a in (st['coords'], bb_ch, aa_ch))
+    assert single.encode_af3(*atoms)
+    ijk_all = single.cube_index()
+    logits = [torch.from_numpy(a).to(cuda) for a in synthetic.synthetic_logits(len(ijk_all), gs + 2 * pad, seed=5)]
+    lut = {tuple(v): n for n, v in enumerate(ijk_all)}
+
+    def model_for(pipe):
+        state = {'b': 0}
+
+        def fn(x, af):
+            rows = [lut[tuple(v)] for v in pipe.ijk_host[state['b']:state['b'] + x.shape[0]]]
+            state['b'] += x.shape[0]
+            idx = torch.tensor(rows, device=cuda)
+            return tuple(t[idx] for t in logits)
+        return fn
+
+    want = single.predict_and_stitch(model_for(single))
+
+    # ---- emulated ranks
+    pipes = [SlabPipeline(cuda, r, world, gs, pad, batch_cubes=4, global_src_shape=src_shape) for r in range(world)]
+    res, owned = [], []
+    for p in pipes:
+        p._exchange = lambda own, p=p: d_src[p.plan.ranks[p.rank].src_lo:p.plan.ranks[p.rank].src_hi].contiguous()
+        # each rank is handed its own block of source planes; the plan is rebuilt inside slab_resample
+        pl = SlabPlan(src_shape, hdr.voxel_size, gs, pad, world)
+        me = pl.ranks[p.rank]
+        r_, o_ = p.slab_resample(d_src[me.own_lo:me.own_hi].contiguous(), hdr)
+        res.append(r_)
+        owned.append(o_)
+    stats = _lockstep_stats(pipes, owned, int(np.prod(n_out)))
+    got_norm = torch.empty(n_out, device=cuda)
+    vols = {k: torch.zeros_like(v) for k, v in want.as_dict().items()}
+    for p, r_, s in zip(pipes, res, stats):
+        p.stats = s
+        p.slab_normalize(r_)
+        assert p.check_status()
+        assert p.median == single.median and p.p999 == single.p999       # thresholds agree exactly
+        me = p.plan.ranks[p.rank]
+        got_norm[me.out_lo:me.out_hi] = p.normalized[me.out_lo - me.ext_lo:me.out_hi - me.ext_lo]
+        assert p.encode_af3(*atoms)
+        v = p.predict_and_stitch(model_for(p))
+        (o0, o1, o2), (e0, e1, e2) = p.box
+        for k, t in v.as_dict().items():
+            vols[k][..., o2:o2 + e2] = t
+    assert (got_norm - single.normalized).abs().max().item() <= 1e-6
+    for k, t in want.as_dict().items():
+        if k == 'amino_acid_prediction':
+            assert (vols[k] == t).float().mean().item() == 1.0
+        else:
+            assert torch.equal(vols[k], t), k          # same logits, same cores -> identical volumes
+    o_norm, _, _ = orc.normalize(orc.resample(src, hdr.voxel_size))
+    assert np.abs(got_norm.cpu().numpy() - o_norm).max() <= 1e-5
