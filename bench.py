@@ -208,7 +208,12 @@ def run_ours(args):
     ops.require_gpu()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner on stdout; the contract is ONE JSON line there
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group('nccl', device_id=dev)
 
     # ---------------- synthetic inputs (host), seed 2022
@@ -216,7 +221,8 @@ def run_ours(args):
     src_np = synthetic.synthetic_map((e, e, e), voxel=args.voxel, seed=2022 + rank)
     header = MapHeader(voxel_size=(np.float32(args.voxel),) * 3)
     n_out = ops.zoom_output_shape(src_np.shape, [np.float32(args.voxel)] * 3)
-    st = synthetic.synthetic_structure(20000, n_out[::-1], seed=2022 + rank)
+    # atoms are replicated on every rank (a few MB) and span the whole (stacked) working grid
+    st = synthetic.synthetic_structure(20000 * world, (n_out[2], n_out[1], n_out[0] * world), seed=2022)
     bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
     src_host = torch.from_numpy(src_np).pin_memory()
     atoms_host = (torch.from_numpy(st['coords']).pin_memory(), torch.from_numpy(bb_ch).pin_memory(),
@@ -228,6 +234,9 @@ def run_ours(args):
         from mica_b200.slab import SlabPipeline
         pipe = SlabPipeline(dev, rank, world, grid_size=args.grid_size, padding=args.padding,
                             batch_cubes=args.batch_cubes)
+        # the stacked map is not cubic: use the geometrically meant clip bounds instead of the
+        # reference's (z,y,x)-vs-(x,y,z) mix-up (D7), which would squash every atom onto z <= nx-1
+        pipe.af3_clip = (n_out[2] - 1, n_out[1] - 1, n_out[0] * world - 1)
     else:
         pipe = MapPipeline(dev, grid_size=args.grid_size, padding=args.padding, batch_cubes=args.batch_cubes)
 
@@ -342,7 +351,10 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_baseline(args)
-    print(json.dumps(line))
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -106,6 +106,8 @@ class MapPipeline:
         self.norm_status = None
         self._x = self._af = None
         self.timer = _no_timer      # bench.py swaps in a StageTimer
+        #: upper clip bounds for the (x,y,z) atom indices; None = the reference's (nz-1,ny-1,nx-1) quirk (D7)
+        self.af3_clip = None
 
     # ------------------------------------------------------------------ stage 1+2
     def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
@@ -149,7 +151,8 @@ class MapPipeline:
         if self.normalized is None:
             raise MicaError('encode_af3 needs the normalised map (its shape and origin)')
         with self.timer('af3_encode'):
-            vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, tuple(self.normalized.shape))
+            vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, tuple(self.normalized.shape),
+                                         clip_hi_xyz=self.af3_clip)
         self.af3, self._af3_status = vol, status
         if defer_status:
             return True

@@ -186,8 +186,8 @@ class SlabPipeline(MapPipeline):
     def encode_af3(self, coords, bb_ch, aa_ch, defer_status=False):
         nz, ny, nx = self.plan.out_shape
         with self.timer('af3_encode'):
-            vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, (nz, ny, nx), z0=self.z0,
-                                         nz_local=self.normalized.shape[0])
+            vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, (nz, ny, nx),
+                                         clip_hi_xyz=self.af3_clip, z0=self.z0, nz_local=self.normalized.shape[0])
         self.af3, self._af3_status = vol, status
         if defer_status:
             return True

@@ -39,7 +39,9 @@ HEAVY_ATOMS = {
 def synthetic_structure(n_residues, box_xyz, seed=2022, origin_xyz=(0.0, 0.0, 0.0),
                         margin=4.0, hetero_every=0, unknown_every=0):
     """Random-walk C-alpha chain (3.8 A steps, reflected at the box walls) with a
-    full heavy-atom set per residue scattered within ~4 A of its C-alpha.
+    full heavy-atom set per residue scattered within ~4 A of its C-alpha (atoms are kept
+    inside the box: on a non-cubic grid the reference's clip quirk D7 turns an atom beyond
+    the x range into an IndexError).
 
     Returns dict(coords float32 [A,3] in (x,y,z) Angstrom, atom_names [A],
     res_names [A], res_ids int [A], hetero bool [A]).  Coordinates are rounded to
@@ -78,7 +80,7 @@ def synthetic_structure(n_residues, box_xyz, seed=2022, origin_xyz=(0.0, 0.0, 0.
         res_names += [name] * len(names)
         res_ids += [r + 1] * len(names)
         hetero += [is_het] * len(names)
-    coords = np.concatenate(coords) + np.asarray(origin_xyz, dtype=np.float64)
+    coords = np.clip(np.concatenate(coords), 0.0, box - 1.0) + np.asarray(origin_xyz, dtype=np.float64)
     coords = np.round(coords, 3).astype(np.float32)
     return dict(coords=coords, atom_names=atom_names, res_names=res_names,
                 res_ids=np.asarray(res_ids), hetero=np.asarray(hetero, dtype=bool))
