@@ -151,6 +151,73 @@ def af3_encode(coords: torch.Tensor, bb_ch: torch.Tensor, aa_ch: torch.Tensor, o
     return out, status
 
 
+class Af3CubeFiller:
+    """Sparse AF3 path (R4 + R5 fused): keeps a [n_slots,24,W,W,W] model-input buffer equal to
+    "zeros + the atoms of the cube currently in each slot" without ever building the dense
+    24-channel volume.  ``bin`` once per map, ``fill`` once per batch."""
+
+    def __init__(self, device, n_slots, grid_size=48, padding=8, perm=(2, 1, 0)):
+        self.device, self.n_slots = device, int(n_slots)
+        self.grid_size, self.padding, self.perm = int(grid_size), int(padding), tuple(perm)
+        W = self.grid_size + 2 * self.padding
+        self.buffer = torch.zeros((self.n_slots, 24, W, W, W), dtype=torch.float32, device=device)
+        self.slot_state = torch.full((self.n_slots,), -1, dtype=torch.int32, device=device)
+        self.status = torch.zeros(1, dtype=torch.int32, device=device)
+        self.ws = None
+        self._geom = None
+        self._dirty = False
+
+    def _fill(self, ijk_ptr, n_slots, nonzero_ptr):
+        n_atoms, (nz, ny, nx) = self._geom
+        check(lib.mica_af3_fill_cubes(C.c_void_p(self.ws.data_ptr()), n_atoms, nz, ny, nx, _lib.int3(self.perm),
+                                      self.grid_size, self.padding, ijk_ptr, n_slots,
+                                      C.c_void_p(self.buffer.data_ptr()), self.buffer.stride(0),
+                                      C.c_void_p(self.slot_state.data_ptr()), nonzero_ptr, _stream()),
+              'af3_fill_cubes')
+
+    def clear(self):
+        """Un-scatter every slot (buffer back to all zeros)."""
+        if self._dirty and self.ws is not None:
+            self._fill(None, self.n_slots, None)
+        self._dirty = False
+
+    def bin(self, coords, bb_ch, aa_ch, origin_xyz, shape_zyx, clip_hi_xyz=None):
+        """Bin the atoms per cube (global cube grid of ``shape_zyx``).  Returns the device
+        status word (1 == the reference's IndexError path, as af3_encode)."""
+        self.clear()                                   # with the OLD bins, before they are rebuilt
+        nz, ny, nx = (int(v) for v in shape_zyx)
+        if clip_hi_xyz is None:
+            clip_hi_xyz = (nz - 1, ny - 1, nx - 1)
+        n = int(coords.shape[0])
+        nbytes = lib.mica_af3_bins_workspace_bytes(n, nz, ny, nx, _lib.int3(self.perm), self.grid_size, self.padding)
+        if nbytes == 0:
+            raise _lib.MicaError(f'af3 bins: {_lib.last_error()}')
+        if self.ws is None or self.ws.numel() < nbytes:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        p_xyz = _dev(coords, torch.float32, 'coords') if n else None
+        p_bb = _dev(bb_ch, torch.int8, 'bb_ch') if n else None
+        p_aa = _dev(aa_ch, torch.int8, 'aa_ch') if n else None
+        ox, oy, oz = (float(np.float32(v)) for v in origin_xyz)
+        check(lib.mica_af3_bin_atoms(p_xyz, p_bb, p_aa, n, ox, oy, oz, int(clip_hi_xyz[0]), int(clip_hi_xyz[1]),
+                                     int(clip_hi_xyz[2]), nz, ny, nx, _lib.int3(self.perm), self.grid_size,
+                                     self.padding, C.c_void_p(self.ws.data_ptr()), self.ws.numel(),
+                                     C.c_void_p(self.status.data_ptr()), _stream()), 'af3_bin_atoms')
+        self._geom = (n, (nz, ny, nx))
+        return self.status
+
+    def fill(self, ijk: torch.Tensor, nonzero: torch.Tensor | None = None) -> torch.Tensor:
+        """AF3 channels of the cubes ``ijk`` (int32 [B,3], B <= n_slots) -> view [B,24,W,W,W]."""
+        B = int(ijk.shape[0])
+        if B > self.n_slots:
+            raise _lib.MicaError(f'batch of {B} cubes exceeds the {self.n_slots} slots')
+        if self._geom is None:
+            raise _lib.MicaError('Af3CubeFiller.fill before bin')
+        p_nz = _dev(nonzero, torch.int32, 'nonzero') if nonzero is not None else None
+        self._fill(_dev(ijk, torch.int32, 'ijk'), B, p_nz)
+        self._dirty = True
+        return self.buffer[:B]
+
+
 # ------------------------------------------------------------ R5/R6 cube extract
 def cube_space_shape(shape_zyx, perm=STANDARD_PERM):
     return tuple(int(shape_zyx[p]) for p in perm)

@@ -92,7 +92,7 @@ class MapPipeline:
     """One GPU's share of the hot path.  With ``slab`` left None it owns the whole map."""
 
     def __init__(self, device, grid_size: int = 48, padding: int = 8, order: int = 3,
-                 batch_cubes: int = 16, target_voxel_size: float = 1.0):
+                 batch_cubes: int = 16, target_voxel_size: float = 1.0, af3_mode: str = 'sparse'):
         ops.require_gpu()
         self.device = torch.device(device)
         self.grid_size, self.padding, self.order = int(grid_size), int(padding), int(order)
@@ -108,6 +108,13 @@ class MapPipeline:
         self.timer = _no_timer      # bench.py swaps in a StageTimer
         #: upper clip bounds for the (x,y,z) atom indices; None = the reference's (nz-1,ny-1,nx-1) quirk (D7)
         self.af3_clip = None
+        #: 'sparse' = AF3 channels of each batch written straight from binned atoms (no dense volume);
+        #: 'dense'  = the reference's dataflow: dense 24-channel volume, then window extraction
+        if af3_mode not in ('sparse', 'dense'):
+            raise MicaError(f'af3_mode must be sparse or dense, got {af3_mode!r}')
+        self.af3_mode = af3_mode
+        self._filler = None
+        self._atoms_binned = False
 
     # ------------------------------------------------------------------ stage 1+2
     def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
@@ -150,15 +157,30 @@ class MapPipeline:
         succeeded (no IndexError from the mis-ordered clip, D7)."""
         if self.normalized is None:
             raise MicaError('encode_af3 needs the normalised map (its shape and origin)')
+        if self.af3_mode == 'sparse':
+            perm, _ = self.header.transpose_order()
+            f = self._filler
+            if f is None or f.perm != tuple(perm) or f.n_slots < self.batch_cubes:
+                self._filler = f = ops.Af3CubeFiller(self.device, self.batch_cubes, self.grid_size, self.padding, perm)
+            with self.timer('af3_bin_atoms'):
+                status = f.bin(coords, bb_ch, aa_ch, self.header.origin, self._global_shape(), self.af3_clip)
+            self.af3, self._af3_status, self._atoms_binned = None, status, True
+            if defer_status:
+                return True
+            self._atoms_binned = int(status.item()) == 0
+            return self._atoms_binned
         with self.timer('af3_encode'):
             vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, tuple(self.normalized.shape),
                                          clip_hi_xyz=self.af3_clip)
-        self.af3, self._af3_status = vol, status
+        self.af3, self._af3_status, self._atoms_binned = vol, status, False
         if defer_status:
             return True
         ok = int(status.item()) == 0
         self.af3 = vol if ok else None
         return ok
+
+    def _global_shape(self):
+        return tuple(self.normalized.shape)
 
     # -------------------------------------------------------------------- stage 4
     def cube_index(self):
@@ -173,22 +195,32 @@ class MapPipeline:
         W = self.window
         if self._x is None or self._x.shape[0] < B:
             self._x = torch.empty((B, 1, W, W, W), dtype=torch.float32, device=self.device)
-            self._af = torch.empty((B, 24, W, W, W), dtype=torch.float32, device=self.device)
             self._nz = torch.empty(B, dtype=torch.int32, device=self.device)
-        return self._x[:B], self._af[:B], self._nz[:B]
+        return self._x[:B], self._nz[:B]
+
+    def _af_buffer(self, B):
+        W = self.window
+        if self._af is None or self._af.shape[0] < B:
+            self._af = torch.empty((B, 24, W, W, W), dtype=torch.float32, device=self.device)
+        return self._af[:B]
 
     def extract_batch(self, b0: int, b1: int, want_flags: bool = False):
         """Cubes [b0,b1) -> (exp_map [B,1,W,W,W], af_features [B,24,W,W,W][, nonzero flags])
         -- the two tensors MICA.forward takes (models/model.py:331)."""
-        x, af, nzf = self._buffers(b1 - b0)
+        x, nzf = self._buffers(b1 - b0)
         ijk = self.ijk[b0:b1]
         with self.timer('extract_map'):
             ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x)
-        if self.af3 is not None:
+        if self._atoms_binned:
+            with self.timer('af3_fill_cubes'):
+                af = self._filler.fill(ijk, nzf if want_flags else None)
+        elif self.af3 is not None:
+            af = self._af_buffer(b1 - b0)
             with self.timer('extract_af3'):
                 ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
                                   nonzero=nzf if want_flags else None)
         else:
+            af = self._af_buffer(b1 - b0)
             af.zero_()                                         # dataset/dataset.py:218-219
             if want_flags:
                 nzf.zero_()
@@ -220,7 +252,7 @@ class MapPipeline:
         if atoms is not None:
             self.encode_af3(*atoms, defer_status=True)
         else:
-            self.af3 = None
+            self.af3, self._atoms_binned = None, False
         vols = self.predict_and_stitch(model_fn, vols)
         # one host read-back for the whole path (the reference reports these per stage)
         if not self.check_status():

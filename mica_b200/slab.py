@@ -127,8 +127,8 @@ class SlabPipeline(MapPipeline):
     of source planes (global planes [own_lo, own_hi) of ``global_src_shape``)."""
 
     def __init__(self, device, rank, world, grid_size=48, padding=8, order=3, batch_cubes=16,
-                 target_voxel_size=1.0, halo_k=16, global_src_shape=None, group=None):
-        super().__init__(device, grid_size, padding, order, batch_cubes, target_voxel_size)
+                 target_voxel_size=1.0, halo_k=16, global_src_shape=None, group=None, af3_mode='sparse'):
+        super().__init__(device, grid_size, padding, order, batch_cubes, target_voxel_size, af3_mode)
         self.rank, self.world, self.halo_k, self.group = int(rank), int(world), halo_k, group
         self.global_src_shape = global_src_shape
         self.plan = None
@@ -183,12 +183,17 @@ class SlabPipeline(MapPipeline):
         self.slab_normalize(res)
         return True if defer_status else self.check_status()
 
+    def _global_shape(self):
+        return tuple(self.plan.out_shape)
+
     def encode_af3(self, coords, bb_ch, aa_ch, defer_status=False):
+        if self.af3_mode == 'sparse':            # atoms are binned on the global cube grid
+            return super().encode_af3(coords, bb_ch, aa_ch, defer_status)
         nz, ny, nx = self.plan.out_shape
         with self.timer('af3_encode'):
             vol, status = ops.af3_encode(coords, bb_ch, aa_ch, self.header.origin, (nz, ny, nx),
                                          clip_hi_xyz=self.af3_clip, z0=self.z0, nz_local=self.normalized.shape[0])
-        self.af3, self._af3_status = vol, status
+        self.af3, self._af3_status, self._atoms_binned = vol, status, False
         if defer_status:
             return True
         ok = int(status.item()) == 0
@@ -210,16 +215,21 @@ class SlabPipeline(MapPipeline):
         return self.ijk_host
 
     def extract_batch(self, b0, b1, want_flags=False):
-        x, af, nzf = self._buffers(b1 - b0)
+        x, nzf = self._buffers(b1 - b0)
         ijk = self.ijk[b0:b1]
         with self.timer('extract_map'):
             ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x,
                               global_nz=self.global_nz, z0=self.z0)
-        if self.af3 is not None:
+        if self._atoms_binned:
+            with self.timer('af3_fill_cubes'):
+                af = self._filler.fill(ijk, nzf if want_flags else None)
+        elif self.af3 is not None:
+            af = self._af_buffer(b1 - b0)
             with self.timer('extract_af3'):
                 ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
                                   global_nz=self.global_nz, z0=self.z0, nonzero=nzf if want_flags else None)
         else:
+            af = self._af_buffer(b1 - b0)
             af.zero_()
             if want_flags:
                 nzf.zero_()

@@ -190,6 +190,55 @@ def test_af3_encode_empty(cuda):
     assert vol.shape == (24, 8, 9, 10) and float(vol.abs().sum()) == 0 and int(status.item()) == 0
 
 
+# ------------------------------------------------- R4 + R5 fused: sparse AF3 cube fill
+@pytest.mark.parametrize('shape,gs,pad,axes', [((40, 40, 40), 32, 16, (1, 2, 3)), ((50, 100, 70), 48, 8, (1, 2, 3)),
+                                               ((64, 48, 32), 48, 8, (2, 3, 1)), ((21, 30, 17), 8, 2, (3, 1, 2))])
+def test_sparse_af3_cube_fill_equals_dense_extract(cuda, shape, gs, pad, axes):
+    """fill(bin(atoms)) == extract_cubes(af3_encode(atoms)) bit for bit, across slot reuse."""
+    nz, ny, nx = shape
+    origin = (np.float32(3.5), np.float32(-2.25), np.float32(0.0))
+    st = synthetic.synthetic_structure(400, (min(nx, nz), ny, min(nx, nz)), seed=nx, origin_xyz=origin, margin=0.0,
+                                       hetero_every=11, unknown_every=6)
+    keep = ~st['hetero']
+    bb, aa = orc.channel_codes([a for a, k in zip(st['atom_names'], keep) if k],
+                               [r for r, k in zip(st['res_names'], keep) if k])
+    coords = st['coords'][keep]
+    d_atoms = (dev(coords, cuda), dev(bb, cuda), dev(aa, cuda))
+    vol, status = ops.af3_encode(*d_atoms, origin, shape)
+    assert int(status.item()) == 0
+    perm, _ = orc.transpose_order(*axes, (0, 0, 0))
+    ijk = ops.cube_origins(ops.cube_space_shape(shape, perm), gs)
+    d_ijk = dev(ijk, cuda)
+    filler = ops.Af3CubeFiller(cuda, 5, gs, pad, perm)
+    assert int(filler.bin(*d_atoms, origin, shape).item()) == 0
+    order = np.random.default_rng(1).permutation(len(ijk))          # arbitrary batch composition
+    d_ijk = d_ijk[torch.from_numpy(order).to(cuda)].contiguous()
+    for b0 in range(0, len(ijk), 5):
+        sub = d_ijk[b0:b0 + 5].contiguous()
+        nzf = torch.empty(len(sub), dtype=torch.int32, device=cuda)
+        got = filler.fill(sub, nzf)
+        want = ops.extract_cubes(vol, sub, gs, pad, perm)
+        assert torch.equal(got, want), b0
+        assert torch.equal(nzf != 0, want.reshape(len(sub), -1).abs().sum(1) > 0)
+    filler.clear()
+    assert float(filler.buffer.abs().sum()) == 0.0                   # un-scatter restores all zeros
+    # re-bin with other atoms: the buffer must follow
+    d2 = (d_atoms[0][::2].contiguous() + 1.0, d_atoms[1][::2].contiguous(), d_atoms[2][::2].contiguous())
+    vol2, _ = ops.af3_encode(*d2, origin, shape)
+    filler.fill(d_ijk[:3].contiguous())
+    filler.bin(*d2, origin, shape)
+    assert torch.equal(filler.fill(d_ijk[:4].contiguous()), ops.extract_cubes(vol2, d_ijk[:4].contiguous(), gs, pad, perm))
+
+
+def test_sparse_af3_reports_the_index_error_path(cuda):
+    origin = (np.float32(0), np.float32(0), np.float32(0))
+    coords = dev(np.array([[65.2, 10.0, 20.0]], np.float32), cuda)
+    bb, aa = dev(np.array([0], np.int8), cuda), dev(np.array([4], np.int8), cuda)
+    f = ops.Af3CubeFiller(cuda, 2, 48, 8)
+    assert int(f.bin(coords, bb, aa, origin, (50, 100, 70)).item()) == 0       # silently mis-clamped (D7 i)
+    assert int(f.bin(coords, bb, aa, origin, (70, 100, 50)).item()) == 1       # IndexError path (D7 ii)
+
+
 # ------------------------------------------------------------ R5/R6 cube extract
 def _extract(vol, cuda, grid_size, padding, axes=(1, 2, 3), transpose=True):
     if transpose:
