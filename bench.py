@@ -47,10 +47,14 @@ def parse_args():
     ap.add_argument('--voxel', type=float, default=1.2)
     ap.add_argument('--grid-size', type=int, default=32)
     ap.add_argument('--padding', type=int, default=16)
-    ap.add_argument('--batch-cubes', type=int, default=32)
+    ap.add_argument('--batch-cubes', type=int, default=128)
     ap.add_argument('--cpu-edge', type=int, default=0, help='source edge of the CPU sample (0 = auto)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--af3-mode', default='sparse', choices=['sparse', 'dense'],
+                    help='sparse: AF3 cube channels written from per-cube atom bins (default); dense: the '
+                         "reference's dataflow (24-channel volume, then window extraction)")
+    ap.add_argument('--no-variant', action='store_true', help='skip timing the other af3 mode')
     return ap.parse_args()
 
 
@@ -197,7 +201,7 @@ def run_ours(args):
     import torch.distributed as dist
     from mica_b200 import ops, synthetic
     from mica_b200.pdb import channel_codes
-    from mica_b200.pipeline import MapHeader, MapPipeline, StageTimer, run_map_pipeline_host
+    from mica_b200.pipeline import MapHeader, MapPipeline, StageTimer, _no_timer, run_map_pipeline_host
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -230,15 +234,17 @@ def run_ours(args):
     src = src_host.to(dev)
     atoms = tuple(t.to(dev) for t in atoms_host)
 
-    if world > 1:
-        from mica_b200.slab import SlabPipeline
-        pipe = SlabPipeline(dev, rank, world, grid_size=args.grid_size, padding=args.padding,
-                            batch_cubes=args.batch_cubes)
-        # the stacked map is not cubic: use the geometrically meant clip bounds instead of the
-        # reference's (z,y,x)-vs-(x,y,z) mix-up (D7), which would squash every atom onto z <= nx-1
-        pipe.af3_clip = (n_out[2] - 1, n_out[1] - 1, n_out[0] * world - 1)
-    else:
-        pipe = MapPipeline(dev, grid_size=args.grid_size, padding=args.padding, batch_cubes=args.batch_cubes)
+    def make_pipe(af3_mode):
+        if world > 1:
+            from mica_b200.slab import SlabPipeline
+            p = SlabPipeline(dev, rank, world, grid_size=args.grid_size, padding=args.padding,
+                             batch_cubes=args.batch_cubes, af3_mode=af3_mode)
+            # the stacked map is not cubic: use the geometrically meant clip bounds instead of the
+            # reference's (z,y,x)-vs-(x,y,z) mix-up (D7), which would squash every atom onto z <= nx-1
+            p.af3_clip = (n_out[2] - 1, n_out[1] - 1, n_out[0] * world - 1)
+            return p
+        return MapPipeline(dev, grid_size=args.grid_size, padding=args.padding, batch_cubes=args.batch_cubes,
+                           af3_mode=af3_mode)
 
     # ---------------- logits ring (stands where MICA.forward stands), >> L2
     W, B = args.grid_size + 2 * args.padding, args.batch_cubes
@@ -252,81 +258,117 @@ def run_ours(args):
         b = x.shape[0]
         return bb[:b], ca[:b], aa[:b]
 
-    vols = None
-
-    def step():
-        nonlocal vols
-        vols = pipe.run(src, header, atoms, model_fn, vols)
-
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    sync()
-    timer = StageTimer()
-    pipe.timer = timer
-    launches0 = ops.launch_count()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    ev0.record()
-    for _ in range(args.steps):
-        step()
-    ev1.record()
-    sync()
-    ms = ev0.elapsed_time(ev1)
-    launches = ops.launch_count() - launches0
-    clk = clocks.stop() if clocks else None
-    stages = timer.summary()
-    pipe.timer = __import__('mica_b200.pipeline', fromlist=['_no_timer'])._no_timer
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    def measure(pipe, with_clocks):
+        """W warm-up steps, then exactly K timed steps between barrier+synchronize, CUDA events on the
+        launching stream, max over ranks."""
+        vols = None
+        for _ in range(args.warmup):
+            vols = pipe.run(src, header, atoms, model_fn, vols)
+        sync()
+        timer = StageTimer()
+        pipe.timer = timer
+        launches0 = ops.launch_count()
+        clocks = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        ev0.record()
+        for _ in range(args.steps):
+            vols = pipe.run(src, header, atoms, model_fn, vols)
+        ev1.record()
+        sync()
+        ms = ev0.elapsed_time(ev1)
+        launches = ops.launch_count() - launches0
+        clk = clocks.stop() if clocks else None
+        stages = timer.summary()
+        pipe.timer = _no_timer
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / args.steps, stages, launches, clk, vols
+
+    pipe = make_pipe(args.af3_mode)
+    ms_per_step, stages, launches, clk, vols = measure(pipe, True)
     n_vox_rank = int(np.prod(pipe.normalized.shape)) if world == 1 else pipe.owned_voxels
     n_vox = n_vox_rank * world
-    ms_per_step = ms / args.steps
     value = n_vox / (ms_per_step * 1e-3) / 1e9
+    n_cubes = len(pipe.ijk_host)
+
+    variant = None
+    if not args.no_variant and world == 1:
+        other = 'dense' if args.af3_mode == 'sparse' else 'sparse'
+        del vols
+        vols = None
+        pipe2 = make_pipe(other)
+        ms2, stages2, _, _, vols2 = measure(pipe2, False)
+        variant = {'af3_mode': other, 'ms_per_step': ms2, 'value': n_vox / (ms2 * 1e-3) / 1e9, 'unit': UNIT,
+                   'stage_ms_per_step': {k: round(v[1] / args.steps, 4) for k, v in stages2.items()}}
+        del pipe2, vols2
+        torch.cuda.empty_cache()
+        vols = pipe.run(src, header, atoms, model_fn, None)
 
     # ---------------- end to end through the public API with host buffers
-    e2e = None
-    if world == 1:
-        out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in vols.as_dict().items()}
-        run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)       # warm
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            _, h2d, d2h = run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        e2e = {'value': n_vox / dt / 1e9, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d),
-               'd2h_bytes_per_step': int(d2h), 'ms_per_step': dt * 1e3,
-               'note': 'pinned host map + atoms -> device -> four stitched volumes -> pinned host'}
+    # (every rank copies its own source block in and its own slab of the four volumes out)
+    out_host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in vols.as_dict().items()}
+    del vols
+    run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)       # warm
+    sync()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        _, h2d, d2h = run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out_host)
+    sync()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {'value': n_vox / dt / 1e9, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d) * world,
+           'd2h_bytes_per_step': int(d2h) * world, 'ms_per_step': dt * 1e3,
+           'note': 'pinned host map + atoms -> device -> four stitched volumes -> pinned host; '
+                   'host wall clock between device synchronisations, max over ranks'}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---------------- roofline of the dominant kernel (AF3-channel cube extract)
+    # ---------------- roofline of the dominant kernel (the single-kernel stage with the most time)
     peak, peak_src = peaks()
     S = args.grid_size
     f = (W / S) ** 3
     n_src = src.numel()
     n_atoms = atoms[0].shape[0]
     alg = algorithmic_bytes(n_src, n_vox_rank, n_atoms, f)
-    calls, tot_ms = stages.get('extract_af3', (0, 0.0))
-    n_cubes = len(pipe.ijk_host)
-    per_launch_bytes = 24 * 4 * (S ** 3 + W ** 3) * (n_cubes / max(1, calls / args.steps))
-    dur_ms = tot_ms / max(1, calls)
-    achieved = per_launch_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms else 0.0
     stage_ms = {k: round(v[1] / args.steps, 4) for k, v in stages.items()}
+    # stage -> (kernel, SURVEY 8(d) algorithmic bytes per step of that kernel)
+    single = {
+        'postproc_stitch': ('postproc_stitch_kernel', alg['postproc_stitch'], '208 B/voxel: 29 logit channels of '
+                            'each core voxel read (116 B), 23 output channels written (92 B)'),
+        'extract_af3': ('extract_tma_kernel<4> (24 AF3 channels)', 96 * n_vox_rank * (1 + f),
+                        '96 B/voxel x (1 + f): 24 channels read once, written f = (W/S)^3 times'),
+        'extract_map': ('extract_tma_kernel<4> (map channel)', 4 * n_vox_rank * (1 + f),
+                        '4 B/voxel x (1 + f): map read once, written f = (W/S)^3 times'),
+        'normalize_apply': ('normalize_apply_kernel', 8 * n_vox_rank, '8 B/voxel: read + write in place'),
+    }
+    dom = max((k for k in single if k in stages), key=lambda k: stages[k][1])
+    calls, tot_ms = stages[dom]
+    per_launch_bytes = single[dom][1] / (calls / args.steps)
+    dur_ms = tot_ms / calls
+    achieved = per_launch_bytes / (dur_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.exists(tpath):      # dram bytes per launch from the committed `ncu --set full` capture
+        t = json.load(open(tpath)).get(single[dom][0].split(' ')[0])
+        if t and t.get('batch_cubes') == args.batch_cubes and t.get('grid_size') == S:
+            traffic = t['dram_bytes_per_launch']
     stage_frac = {}
     for name, keys in (('resample', ['resample']), ('normalize', ['order_stats', 'normalize_apply']),
-                       ('af3_encode', ['af3_encode']), ('extract', ['extract_map', 'extract_af3']),
+                       ('af3_encode', ['af3_encode']), ('extract', ['extract_map', 'extract_af3', 'af3_fill_cubes']),
                        ('postproc_stitch', ['postproc_stitch'])):
         t_ms = sum(stage_ms.get(k, 0.0) for k in keys)
         if t_ms:
@@ -339,14 +381,20 @@ def run_ours(args):
         'config': workload_config(args, world) | {'working_grid': list(pipe.normalized.shape), 'cubes': n_cubes,
                                                    'atoms': int(n_atoms)},
         'roofline': {
-            'bound': 'hbm', 'kernel': 'extract_transpose_kernel<0> (24 AF3 channels per cube batch)',
-            'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
-            'peak_source': peak_src, 'launch_ms': dur_ms, 'algorithmic_bytes_per_launch': per_launch_bytes,
+            'bound': 'hbm', 'kernel': single[dom][0], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'frac': achieved / peak, 'traffic': traffic,
+            'peak_source': peak_src, 'launch_ms': dur_ms, 'launches_per_step': calls / args.steps,
+            'algorithmic_bytes_per_launch': per_launch_bytes, 'algorithmic_bytes_rule': single[dom][2],
+            'share_of_step': tot_ms / args.steps / ms_per_step,
+            # the whole path against SURVEY 8(d)'s B(N), which counts the dataflow the reference
+            # materialises (dense 24-channel AF3 volume and its windows); the sparse AF3 path moves
+            # fewer bytes than B(N), so this figure can exceed 1 -- it is not a kernel roofline
             'whole_path': {'algorithmic_bytes_per_voxel': total_alg / n_vox_rank,
                            'achieved': total_alg / (ms_per_step * 1e-3) / 1e9,
                            'frac': total_alg / (ms_per_step * 1e-3) / 1e9 / peak},
             'stage_ms_per_step': stage_ms, 'stage_frac_of_peak': stage_frac,
         },
+        'af3_mode': args.af3_mode, 'variant': variant,
         'clocks': clk, 'gpu_launches': int(launches), 'e2e': e2e,
     }
     if world == 1 and not args.no_cpu_baseline:

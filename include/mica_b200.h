@@ -66,6 +66,11 @@ int mica_zoom_output_shape(const int in_zyx[3], const float zoom_zyx[3], int out
 /* workspace for a source slab of src_nz_local planes */
 size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, int ny, int nx, int order);
 
+/* test hook: on != 0 routes every shape through the general kernels (one thread per line /
+ * per output voxel) instead of the segment-parallel prefilter and the marching gather.
+ * Returns the previous setting.  Both routes implement the same arithmetic. */
+int mica_resample_force_generic(int on);
+
 /* src: device float32 [src_nz_local, sy, sx] = global source planes [src_z0, src_z0+src_nz_local)
  * dst: device float32 [dst_nz_local, ny, nx] = global output planes [dst_z0, dst_z0+dst_nz_local)
  * (sz,sy,sx) / (nz,ny,nx) are the GLOBAL source / output shapes.  With a partial

@@ -46,6 +46,14 @@ __device__ __forceinline__ float ld_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
+// same, for 128-byte runs that start in the middle of a 128-byte line (cube cores at stride 32):
+// by default a miss makes L2 fetch the whole 128-byte line from DRAM (measured on B200: 2.0x the
+// requested bytes, tools/micro/overfetch.cu); .L2::64B caps the fill at the 64-byte half that is used
+__device__ __forceinline__ float ld_stream_half_line(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ float4 ld_stream4(const float4* p) {
   float4 v;
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -322,8 +322,14 @@ extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_c
                             (cuuint64_t)(n_channels > 1 ? chan_stride : (int64_t)nz_local * ny * nx) * 4};
       cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)kTmaBT, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      if (const char* e = getenv("MICA_TMA_L2PROMO")) {   // experiment knob: 0 none, 1 64B, 2 128B, 3 256B
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+              : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      }
       CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)vol, gdim, gstr, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       if (r == CUDA_SUCCESS) {
         use_tma = true;

@@ -10,11 +10,21 @@
 //
 // Kernels (all HBM-bound, see DESIGN.md for the byte counts):
 //   taps_kernel          per-axis tap index / weight tables (tiny)
-//   prefilter_cols       IIR along a strided axis (z or y): a [n x CW] float64 tile
-//                        of CW neighbouring lines is staged in shared memory with
-//                        coalesced loads, one thread sweeps each line, coalesced store
-//   prefilter_rows       IIR along the contiguous axis (x): [R x n] tile, same idea
-//   gather3 / gather1    64-tap / 8-tap separable gather, x fastest across threads
+//   prefilter_cols_seg   IIR along a strided axis (z or y): a [n x 32] float64 tile of 32
+//   prefilter_rows_seg   neighbouring lines (rows: [32 x n], contiguous axis) is staged in
+//                        shared memory with coalesced loads; every line is cut into 8 segments
+//                        swept concurrently, each warmed up over the kHorizon samples before
+//                        (causal) / after (anticausal) it -- the pole's impulse response has
+//                        decayed below double rounding by then -- so all 256 threads recurse
+//   march3_kernel        separable 4x4x4 gather: a CTA owns an [8 y x 64 x] output column and
+//                        marches along z; each source plane is x-interpolated from global
+//                        memory into shared memory (software-pipelined one plane ahead),
+//                        y-interpolated into a 4-plane register window, and every output
+//                        plane is 4 FMAs from that window: ~4 global + ~4 shared loads per
+//                        output voxel instead of 64 global loads
+//   prefilter_cols / prefilter_rows / gather3 / gather1
+//                        general fall-backs (short or very long lines, strong down-sampling,
+//                        trilinear): one thread per line / one thread per output voxel
 #include "common.cuh"
 
 namespace mica {
@@ -166,6 +176,110 @@ prefilter_rows(double* __restrict__ data, int n, int64_t n_rows) {
   }
 }
 
+
+// ------------------------------------------------- segment-parallel prefilter
+// |pole|^30 = 7e-18: a recursion started kHorizon samples early from a zero state (the samples
+// before index 0 / after n-1 being the mirror images SciPy's boundary rule implies) has
+// forgotten its start to below double rounding when it reaches the segment.
+constexpr int kHorizon = 30;
+constexpr int kSegs = 8;            // segments per line = 256 threads / 32 lines
+constexpr int kMinSegLine = 96;     // shorter lines take the one-thread-per-line kernels
+
+// Filters samples [k0, k1) of one line in place; all threads of the block call this together
+// (three block-wide barriers inside).  `line` points at sample 0, `stride` in doubles.
+__device__ __forceinline__ void iir_segment(double* line, int n, int stride, int k0, int k1, bool active) {
+  const double z = kPole;
+  double st = 0.0;
+  if (active) {   // causal state entering the segment: sum_j z^j s[k0-1-j], mirrored below 0
+    for (int m = kHorizon - 1; m >= 0; --m) {
+      int idx = k0 - 1 - m;
+      idx = idx < 0 ? -idx : idx;
+      st = fma(z, st, line[idx * stride]);
+    }
+  }
+  __syncthreads();   // every warm-up read of raw samples is done before anyone overwrites them
+  if (active) {
+#pragma unroll 4
+    for (int k = k0; k < k1; ++k) {
+      st = fma(z, st, line[k * stride]);
+      line[k * stride] = st;
+    }
+  }
+  __syncthreads();
+  bool at_end = false;
+  if (active) {   // anticausal state just above the segment
+    if (k1 >= n) {
+      at_end = true;
+    } else {
+      int kk = k1 + kHorizon;
+      int k = kk - 1;
+      st = 0.0;
+      if (kk >= n) {  // the exact end initialisation is within reach: start from it
+        st = (z / (z * z - 1.0)) * (line[(n - 1) * stride] + z * line[(n - 2) * stride]);
+        k = n - 2;
+      }
+      for (; k >= k1; --k) st = z * (st - line[k * stride]);
+    }
+  }
+  __syncthreads();
+  if (active) {
+    int k = k1 - 1;
+    if (at_end) {
+      st = (z / (z * z - 1.0)) * (line[(n - 1) * stride] + z * line[(n - 2) * stride]);
+      line[(n - 1) * stride] = st;
+      k = n - 2;
+    }
+#pragma unroll 4
+    for (; k >= k0; --k) {
+      st = z * (st - line[k * stride]);
+      line[k * stride] = st;
+    }
+  }
+}
+
+// lines along a strided axis.  grid = (ceil(n_cols / 32), n_outer), block = 256, tile [n][32]
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+prefilter_cols_seg(const TIn* __restrict__ in, double* __restrict__ out, int n, int64_t line_stride,
+                   int n_cols, int64_t outer_stride) {
+  extern __shared__ double tile[];
+  constexpr int CW = 32;
+  const int col0 = blockIdx.x * CW;
+  const int64_t base = (int64_t)blockIdx.y * outer_stride + col0;
+  const int ncol = min(CW, n_cols - col0);
+  const int j = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  for (int k = seg; k < n; k += kSegs)
+    if (j < ncol) tile[k * CW + j] = (double)in[base + (int64_t)k * line_stride + j] * kGain;
+  __syncthreads();
+  const int len = (n + kSegs - 1) / kSegs;
+  const int k0 = seg * len, k1 = min(n, k0 + len);
+  iir_segment(tile + j, n, CW, k0, k1, j < ncol && k0 < k1);
+  __syncthreads();
+  for (int k = seg; k < n; k += kSegs)
+    if (j < ncol) out[base + (int64_t)k * line_stride + j] = tile[k * CW + j];
+}
+
+// lines along the contiguous axis.  grid = ceil(n_rows / 32), block = 256, tile [32][n | 1]
+__global__ void __launch_bounds__(256)
+prefilter_rows_seg(double* __restrict__ data, int n, int64_t n_rows) {
+  extern __shared__ double tile[];
+  constexpr int R = 32;
+  const int pitch = n | 1;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+  const int nrow = (int)min((int64_t)R, n_rows - row0);
+  double* g = data + row0 * n;
+  for (int r = threadIdx.x >> 5; r < nrow; r += 8)
+    for (int k = threadIdx.x & 31; k < n; k += 32) tile[r * pitch + k] = g[(int64_t)r * n + k] * kGain;
+  __syncthreads();
+  const int r = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int len = (n + kSegs - 1) / kSegs;
+  const int k0 = seg * len, k1 = min(n, k0 + len);
+  iir_segment(tile + r * pitch, n, 1, k0, k1, r < nrow && k0 < k1);
+  __syncthreads();
+  for (int rr = threadIdx.x >> 5; rr < nrow; rr += 8)
+    for (int k = threadIdx.x & 31; k < n; k += 32) g[(int64_t)rr * n + k] = tile[rr * pitch + k];
+}
+
 // fallback for lines too long for shared memory: sweep in global memory
 template <typename TIn>
 __global__ void prefilter_cols_global(const TIn* __restrict__ in, double* __restrict__ out, int n,
@@ -233,6 +347,142 @@ gather3_kernel(const double* __restrict__ c, int sy, int sx, const Tap* __restri
   st_stream(dst + ((int64_t)z * ny + y) * nx + x, (float)acc);
 }
 
+
+// ---------------------------------------------------------- marching gather
+// Per output plane: the four (mirrored) z taps folded into one contiguous 4-plane window
+// [base, base+3] of local source planes, weights of coinciding planes merged.
+struct ZWin {
+  int base;
+  int pad;
+  double w[4];
+};
+
+__global__ void zwin_kernel(const Tap* __restrict__ tz, ZWin* __restrict__ zw, int n, int in_local) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Tap t = tz[i];
+  int base = 0x7fffffff;
+  for (int l = 0; l < 4; ++l)
+    if (t.w[l] != 0.0) base = min(base, t.idx[l]);
+  // all-zero taps (D11) only occur past the end of the map: park the window at the last planes so
+  // that `base` stays non-decreasing along z (the march emits a plane when its window is loaded)
+  if (base == 0x7fffffff) base = in_local - 4;
+  base = max(0, min(base, in_local - 4));
+  ZWin z;
+  z.base = base;
+  z.pad = 0;
+  for (int j = 0; j < 4; ++j) z.w[j] = 0.0;
+  for (int l = 0; l < 4; ++l) {
+    if (t.w[l] == 0.0) continue;
+    const int j = min(3, max(0, t.idx[l] - base));
+    z.w[j] += t.w[l];
+  }
+  zw[i] = z;
+}
+
+// grid = (ceil(nx / 64), ceil(ny / 8), z chunks), block = 256.  NI * 4 = source rows staged per plane.
+template <int NI>
+__global__ void __launch_bounds__(256)
+march3_kernel(const double* __restrict__ c, int sy, int sx, const ZWin* __restrict__ zw,
+              const Tap* __restrict__ ty, const Tap* __restrict__ tx, float* __restrict__ dst, int ny, int nx,
+              int nz_local, int zchunk) {
+  constexpr int TX = 64, TY = 8, ROWS = NI * 4;
+  __shared__ double A[2][ROWS][TX];
+  __shared__ int s_lo;
+  const int t = threadIdx.x;
+  const int lx = t & (TX - 1), lr = t >> 6;
+  const int x = blockIdx.x * TX + lx;
+  const int y0 = blockIdx.y * TY;
+  const int z_begin = blockIdx.z * zchunk, z_end = min(nz_local, z_begin + zchunk);
+  if (z_begin >= z_end) return;
+
+  // lowest source row any output row of this tile taps (zero-weight rows, D11, excluded)
+  if (t == 0) s_lo = 0x7fffffff;
+  __syncthreads();
+  if (t < TY * 4) {
+    const int r = min(y0 + (t >> 2), ny - 1);
+    if (ty[r].w[t & 3] != 0.0) atomicMin(&s_lo, ty[r].idx[t & 3]);
+  }
+  __syncthreads();
+  const int lo_y = (s_lo == 0x7fffffff) ? 0 : s_lo;
+
+  const Tap Tx = tx[min(x, nx - 1)];
+  int iy[2][4];
+  double wy[2][4];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const Tap T = ty[min(y0 + lr + 4 * o, ny - 1)];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      wy[o][m] = T.w[m];
+      iy[o][m] = (T.w[m] != 0.0) ? min(ROWS - 1, T.idx[m] - lo_y) : 0;
+    }
+  }
+  // source rows this thread x-interpolates: lo_y + lr + 4 i (clamped: rows past sy-1 are never tapped)
+  const int64_t plane = (int64_t)sy * sx;
+  const double* rowp[NI];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) rowp[i] = c + (int64_t)min(lo_y + lr + 4 * i, sy - 1) * sx;
+
+  double v[2][4];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[o][m] = 0.0;
+
+  const int p_start = zw[z_begin].base, p_last = zw[z_end - 1].base + 3;
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    const double* r = rowp[i] + (int64_t)p_start * plane;
+    A[0][lr + 4 * i][lx] = Tx.w[0] * r[Tx.idx[0]] + Tx.w[1] * r[Tx.idx[1]] + Tx.w[2] * r[Tx.idx[2]] +
+                           Tx.w[3] * r[Tx.idx[3]];
+  }
+  __syncthreads();
+
+  int zc = z_begin;
+  int next_emit = zw[zc].base + 3;
+  for (int p = p_start; p <= p_last; ++p) {
+    const int cur = (p - p_start) & 1;
+    const bool more = p < p_last;
+    double raw[NI][4];
+    if (more) {   // issue the next plane's loads before touching shared memory
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const double* r = rowp[i] + (int64_t)(p + 1) * plane;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) raw[i][l] = r[Tx.idx[l]];
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const double vn = wy[o][0] * A[cur][iy[o][0]][lx] + wy[o][1] * A[cur][iy[o][1]][lx] +
+                        wy[o][2] * A[cur][iy[o][2]][lx] + wy[o][3] * A[cur][iy[o][3]][lx];
+      v[o][0] = v[o][1];
+      v[o][1] = v[o][2];
+      v[o][2] = v[o][3];
+      v[o][3] = vn;
+    }
+    while (zc < z_end && next_emit <= p) {
+      const ZWin Wz = zw[zc];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const int y = y0 + lr + 4 * o;
+        const double acc = Wz.w[0] * v[o][0] + Wz.w[1] * v[o][1] + Wz.w[2] * v[o][2] + Wz.w[3] * v[o][3];
+        if (x < nx && y < ny) st_stream(dst + ((int64_t)zc * ny + y) * nx + x, (float)acc);
+      }
+      ++zc;
+      if (zc < z_end) next_emit = zw[zc].base + 3;
+    }
+    if (more) {
+#pragma unroll
+      for (int i = 0; i < NI; ++i)
+        A[cur ^ 1][lr + 4 * i][lx] = Tx.w[0] * raw[i][0] + Tx.w[1] * raw[i][1] + Tx.w[2] * raw[i][2] +
+                                     Tx.w[3] * raw[i][3];
+    }
+    __syncthreads();
+  }
+}
+
 __global__ void __launch_bounds__(128)
 gather1_kernel(const float* __restrict__ src, int sy, int sx, const Tap* __restrict__ tz,
                const Tap* __restrict__ ty, const Tap* __restrict__ tx, float* __restrict__ dst, int ny,
@@ -262,6 +512,8 @@ gather1_kernel(const float* __restrict__ src, int sy, int sx, const Tap* __restr
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int g_force_generic = 0;   // tests: run the general kernels on shapes the fast ones would take
+
 constexpr size_t kMaxTileBytes = 200 * 1024;
 
 template <typename TIn>
@@ -269,7 +521,11 @@ static int launch_cols(const TIn* in, double* out, int n, int64_t line_stride, i
                        int64_t outer_stride, int n_outer, cudaStream_t st) {
   if (n_cols <= 0 || n_outer <= 0 || n <= 0) return MICA_OK;
   size_t per_col = (size_t)n * sizeof(double);
-  if (per_col * 32 <= kMaxTileBytes) {
+  if (!g_force_generic && n >= kMinSegLine && per_col * 32 <= kMaxTileBytes) {
+    size_t smem = per_col * 32;
+    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefilter_cols_seg<TIn><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+  } else if (per_col * 32 <= kMaxTileBytes) {
     size_t smem = per_col * 32;
     MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prefilter_cols<TIn, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
@@ -287,7 +543,11 @@ static int launch_cols(const TIn* in, double* out, int n, int64_t line_stride, i
 static int launch_rows(double* data, int n, int64_t n_rows, cudaStream_t st) {
   if (n <= 0 || n_rows <= 0) return MICA_OK;
   size_t per_row = (size_t)(n | 1) * sizeof(double);
-  if (per_row * 32 <= kMaxTileBytes) {
+  if (!g_force_generic && n >= kMinSegLine && per_row * 32 <= kMaxTileBytes) {
+    size_t smem = per_row * 32;
+    MICA_CUDA(cudaFuncSetAttribute(prefilter_rows_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefilter_rows_seg<<<(unsigned)ceil_div64(n_rows, 32), 256, smem, st>>>(data, n, n_rows);
+  } else if (per_row * 32 <= kMaxTileBytes) {
     size_t smem = per_row * 32;
     MICA_CUDA(cudaFuncSetAttribute(prefilter_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     prefilter_rows<32><<<(unsigned)ceil_div64(n_rows, 32), 256, smem, st>>>(data, n, n_rows);
@@ -316,8 +576,14 @@ extern "C" int mica_zoom_output_shape(const int in_zyx[3], const float zoom_zyx[
   return MICA_OK;
 }
 
+extern "C" int mica_resample_force_generic(int on) {
+  const int was = g_force_generic;
+  g_force_generic = on ? 1 : 0;
+  return was;
+}
+
 extern "C" size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, int ny, int nx, int order) {
-  size_t taps = align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256);
+  size_t taps = align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256) + align_up((size_t)nz * sizeof(ZWin), 256);
   size_t coeff = (order == 3) ? align_up((size_t)src_nz_local * sy * sx * sizeof(double), 256) : 0;
   return taps + coeff + 256;
 }
@@ -340,7 +606,8 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
   Tap* tz = (Tap*)ws;
   Tap* ty = tz + nz;
   Tap* tx = ty + ny;
-  double* coeff = (double*)(ws + align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256));
+  ZWin* zw = (ZWin*)(ws + align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256));
+  double* coeff = (double*)((char*)zw + align_up((size_t)nz * sizeof(ZWin), 256));
 
   taps_kernel<<<(dst_nz_local + 127) / 128, 128, 0, st>>>(tz, dst_nz_local, dst_z0, sz, nz, order, src_z0, src_nz_local);
   MICA_LAUNCH_CHECK("taps_kernel(z)");
@@ -362,8 +629,29 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
     // axis 2 (x): contiguous rows
     rc = launch_rows(coeff, sx, (int64_t)src_nz_local * sy, st);
     if (rc) return rc;
-    gather3_kernel<<<grid, 128, 0, st>>>(coeff, sy, sx, tz, ty, tx, dst, ny, nx);
-    MICA_LAUNCH_CHECK("gather3_kernel");
+    // marching gather when the y span of an 8-row output tile fits the staged rows and every
+    // axis has a full 4-sample window; else one thread per output voxel
+    const double zoom_y = ny > 1 ? (double)(sy - 1) / (double)(ny - 1) : 1.0;
+    const int span_y = (int)floor(7.0 * zoom_y) + 5;
+    if (!g_force_generic && src_nz_local >= 4 && sy >= 4 && sx >= 4 && span_y <= 16) {
+      zwin_kernel<<<(dst_nz_local + 127) / 128, 128, 0, st>>>(tz, zw, dst_nz_local, src_nz_local);
+      MICA_LAUNCH_CHECK("zwin_kernel");
+      const int xt = (nx + 63) / 64, yt = (ny + 7) / 8;
+      int nzc = (8 * kNumSMs + xt * yt - 1) / (xt * yt);
+      nzc = nzc < 1 ? 1 : nzc;
+      if (nzc > (dst_nz_local + 15) / 16) nzc = (dst_nz_local + 15) / 16;
+      const int zchunk = (dst_nz_local + nzc - 1) / nzc;
+      dim3 mgrid(xt, yt, (dst_nz_local + zchunk - 1) / zchunk);
+      MICA_REQUIRE(yt <= 65535 && mgrid.z <= 65535, "output too large for the launch grid");
+      if (span_y <= 12)
+        march3_kernel<3><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+      else
+        march3_kernel<4><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+      MICA_LAUNCH_CHECK("march3_kernel");
+    } else {
+      gather3_kernel<<<grid, 128, 0, st>>>(coeff, sy, sx, tz, ty, tx, dst, ny, nx);
+      MICA_LAUNCH_CHECK("gather3_kernel");
+    }
   } else {
     gather1_kernel<<<grid, 128, 0, st>>>(src, sy, sx, tz, ty, tx, dst, ny, nx);
     MICA_LAUNCH_CHECK("gather1_kernel");

@@ -36,11 +36,13 @@ __device__ __forceinline__ float softmax3_last(float l0, float l1, float l2) {
   return __fdiv_rn(e2, s);
 }
 
-// grid = (S [core plane a], B), block = 256
+// grid = (S [core plane a] * ceil(S*S / 256), B), block = 256: one core voxel per thread, so a batch
+// is thousands of small CTAs and the last wave over the 148 SMs is short
 __global__ void __launch_bounds__(256)
 postproc_stitch_kernel(StitchParams P) {
-  const int a = blockIdx.x, b = blockIdx.y;
   const int S = P.S, W = P.W;
+  const int chunks = (S * S + 255) >> 8;
+  const int a = blockIdx.x / chunks, b = blockIdx.y;
   const int i = P.ijk[3 * b + 0], j = P.ijk[3 * b + 1], k = P.ijk[3 * b + 2];
   const int gx = i + a;
   if (gx >= P.X || gx < P.org[0] || gx >= P.org[0] + P.ext[0]) return;
@@ -49,20 +51,22 @@ postproc_stitch_kernel(StitchParams P) {
   const float* ca = P.ca + (int64_t)b * 4 * W3;
   const float* aa = P.aa + (int64_t)b * 21 * W3;
   const int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
-  for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+  {
+    const int e = (blockIdx.x - a * chunks) * 256 + threadIdx.x;
+    if (e >= S * S) return;
     const int bj = e / S, c = e - bj * S;
     const int gy = j + bj, gz = k + c;
-    if (gy >= P.Y || gz >= P.Z) continue;
+    if (gy >= P.Y || gz >= P.Z) return;
     const int ly = gy - P.org[1], lz = gz - P.org[2];
-    if ((unsigned)ly >= (unsigned)P.ext[1] || (unsigned)lz >= (unsigned)P.ext[2]) continue;
+    if ((unsigned)ly >= (unsigned)P.ext[1] || (unsigned)lz >= (unsigned)P.ext[2]) return;
     const int64_t src = ((int64_t)(a + P.pad) * W + (bj + P.pad)) * W + (c + P.pad);
     const int64_t dst = ((int64_t)(gx - P.org[0]) * P.ext[1] + ly) * P.ext[2] + lz;
     // issue every load before the math: 26 independent requests in flight per thread
-    const float b0 = ld_stream(bb + src), b2 = ld_stream(bb + 2 * W3 + src), b3 = ld_stream(bb + 3 * W3 + src);
-    const float c0 = ld_stream(ca + src), c2 = ld_stream(ca + 2 * W3 + src), c3 = ld_stream(ca + 3 * W3 + src);
+    const float b0 = ld_stream_half_line(bb + src), b2 = ld_stream_half_line(bb + 2 * W3 + src), b3 = ld_stream_half_line(bb + 3 * W3 + src);
+    const float c0 = ld_stream_half_line(ca + src), c2 = ld_stream_half_line(ca + 2 * W3 + src), c3 = ld_stream_half_line(ca + 3 * W3 + src);
     float l[20];
 #pragma unroll
-    for (int t = 0; t < 20; ++t) l[t] = ld_stream(aa + (int64_t)(t + 1) * W3 + src);
+    for (int t = 0; t < 20; ++t) l[t] = ld_stream_half_line(aa + (int64_t)(t + 1) * W3 + src);
     st_stream(P.bb_vol + dst, softmax3_last(b0, b2, b3));
     st_stream(P.ca_vol + dst, softmax3_last(c0, c2, c3));
     float m = l[0];
@@ -108,7 +112,7 @@ stitch_cubes_kernel(const float* __restrict__ cubes, int n_ch, const int32_t* __
     const int ly = gy - o1, lz = gz - o2;
     if ((unsigned)ly >= (unsigned)e1 || (unsigned)lz >= (unsigned)e2) continue;
     const int64_t src = ((int64_t)(a + pad) * W + (bj + pad)) * W + (c + pad);
-    v[((int64_t)(gx - o0) * e1 + ly) * e2 + lz] = ld_stream(cube + src);
+    v[((int64_t)(gx - o0) * e1 + ly) * e2 + lz] = ld_stream_half_line(cube + src);
   }
 }
 
@@ -162,7 +166,8 @@ extern "C" int mica_postproc_stitch(const float* bb, const float* ca, const floa
     P.ca = ca + (int64_t)b0 * 4 * W3;
     P.aa = aa + (int64_t)b0 * 21 * W3;
     P.ijk = ijk + 3 * (int64_t)b0;
-    postproc_stitch_kernel<<<dim3(grid_size, nb), 256, 0, (cudaStream_t)stream>>>(P);
+    const int chunks = (grid_size * grid_size + 255) / 256;
+    postproc_stitch_kernel<<<dim3(grid_size * chunks, nb), 256, 0, (cudaStream_t)stream>>>(P);
     MICA_LAUNCH_CHECK("postproc_stitch_kernel");
   }
   return MICA_OK;

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from mica_b200 import ops, synthetic
+from mica_b200 import _lib, ops, synthetic
 from oracle import mica_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -46,6 +46,53 @@ def test_resample_matches_scipy(cuda, shape, voxel, order):
     got = ops.resample(dev(src, cuda), out_shape, order=order).cpu().numpy()
     scale = float(np.abs(want).max())
     assert np.abs(got - want).max() <= 2e-6 * scale
+
+
+@pytest.mark.parametrize('shape,voxel', [
+    ((100, 104, 98), (1.2, 1.2, 1.2)),       # segment-parallel prefilter + marching gather (3 x 4 staged rows)
+    ((128, 96, 112), (1.06, 1.2, 0.97)),     # anisotropic, mixed up/down-sampling
+    ((150, 100, 97), (0.8, 0.8, 0.8)),       # down-sampling: wider y span (4 x 4 staged rows)
+    ((128, 128, 100), (1.2, 1.2, 1.2)),      # 128 -> 154 overshoots on z and y (D11) on the fast path
+    ((97, 130, 260), (1.31, 1.07, 1.13)),    # ragged tiles: nx, ny not multiples of 64 / 8
+])
+def test_resample_fast_path_matches_scipy_and_general_path(cuda, shape, voxel):
+    rng = np.random.default_rng(hash(shape) % 2**32)
+    src = rng.normal(size=shape).astype(np.float32)
+    voxel = tuple(np.float32(v) for v in voxel)
+    want = orc.resample(src, voxel, order=3)
+    out_shape = ops.zoom_output_shape(shape, orc.zoom_factors(voxel))
+    assert out_shape == want.shape
+    d_src = dev(src, cuda)
+    got = ops.resample(d_src, out_shape).cpu().numpy()
+    was = _lib.lib.mica_resample_force_generic(1)
+    try:
+        general = ops.resample(d_src, out_shape).cpu().numpy()
+    finally:
+        _lib.lib.mica_resample_force_generic(was)
+    scale = float(np.abs(want).max())
+    assert np.abs(got - want).max() <= 2e-6 * scale
+    assert np.abs(general - want).max() <= 2e-6 * scale
+    # the two routes differ only in summation order / the 30-sample warm-up: float32 rounding flips at most
+    assert np.abs(got - general).max() <= 3e-7 * scale
+    if shape == (128, 128, 100):
+        assert not got[-1].any() and not got[:, -1].any() and got[:-1, :-1].any()      # D11 zero faces
+
+
+def test_resample_slab_fast_path(cuda):
+    """A z-slab (source planes + halo in, owned output planes out) on the fast kernels equals
+    the same planes of the whole-volume SciPy result."""
+    shape, voxel = (330, 100, 101), (np.float32(1.2),) * 3
+    src = np.random.default_rng(3).normal(size=shape).astype(np.float32)
+    want = orc.resample(src, voxel, order=3)
+    out_shape = want.shape
+    scale_z = (shape[0] - 1) / (out_shape[0] - 1)
+    scale = float(np.abs(want).max())
+    for lo, hi in ((0, 140), (120, 290), (250, out_shape[0])):
+        s_lo = max(0, int(np.floor(lo * scale_z)) - 1 - 16)
+        s_hi = min(shape[0], int(np.floor((hi - 1) * scale_z)) + 2 + 16 + 1)
+        got = ops.resample(dev(src[s_lo:s_hi], cuda), out_shape, src_z0=s_lo, src_shape=shape,
+                           dst_z0=lo, dst_nz_local=hi - lo).cpu().numpy()
+        assert np.abs(got - want[lo:hi]).max() <= 2e-6 * scale
 
 
 def test_resample_golden_then_normalize_end_to_end(cuda, golden_dir):
