@@ -129,10 +129,13 @@ int mica_af3_encode(const float* xyz, const int8_t* bb_ch, const int8_t* aa_ch, 
  * 24-channel volume (utils/preprocessing.py:268-298 + utils/create_grids.py:269-352 +
  * dataset/dataset.py:209-219 in one step).  mica_af3_bin_atoms bins the atoms per cube
  * once per map (same index arithmetic and clip quirk as mica_af3_encode; status_oob as
- * there); mica_af3_fill_cubes keeps `out` ([n_slots, 24, W^3] at out_cube_stride, which
- * the caller zero-fills ONCE and never writes) equal to "zeros + the atoms of the cube
- * currently in each slot": it clears the voxels of the slot's previous cube and sets those
- * of ijk[slot] (ijk == NULL: clear only).  slot_state: device int32 [n_slots], -1 = clean.
+ * there); mica_af3_fill_cubes keeps `out` ([slots, 24, W^3] at out_cube_stride, which the
+ * caller zero-fills ONCE and never writes) equal to "zeros + the atoms of the cube shown in
+ * each slot": slot b currently shows cube ijk_prev[b] (b < n_prev; clean otherwise) and is
+ * switched to cube ijk_next[b] (b < n_next; left clean otherwise) by clearing the voxels
+ * of the old cube and setting those of the new one.  Stateless: the caller passes what it
+ * passed as ijk_next last time (n_prev = 0 for a fresh buffer; n_next = 0 clears).
+ * nonzero (nullable, int32 [n_next]): 1 iff the cube has any atom voxel.
  * The result is bit-identical to mica_extract_cubes(mica_af3_encode(atoms)).
  */
 size_t mica_af3_bins_workspace_bytes(int64_t n_atoms, int nz, int ny, int nx, const int perm[3],
@@ -142,9 +145,9 @@ int mica_af3_bin_atoms(const float* xyz, const int8_t* bb_ch, const int8_t* aa_c
                        int nz, int ny, int nx, const int perm[3], int grid_size, int padding,
                        void* workspace, size_t workspace_bytes, int* status_oob, mica_stream_t stream);
 int mica_af3_fill_cubes(const void* workspace, int64_t n_atoms, int nz, int ny, int nx, const int perm[3],
-                        int grid_size, int padding, const int32_t* ijk, int n_slots,
-                        float* out, int64_t out_cube_stride, int32_t* slot_state, int32_t* nonzero,
-                        mica_stream_t stream);
+                        int grid_size, int padding, const int32_t* ijk_prev, int n_prev,
+                        const int32_t* ijk_next, int n_next, float* out, int64_t out_cube_stride,
+                        int32_t* nonzero, mica_stream_t stream);
 
 /* --------------------------------------------------------- R5/R6 cube extract
  * Replaces GridCreator.transpose + create_grids_from_mrc (utils/create_grids.py:67-176),

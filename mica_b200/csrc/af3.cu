@@ -166,12 +166,20 @@ af3_bin_kernel(const float* __restrict__ xyz, const int8_t* __restrict__ bb_ch, 
     for (int c1 = lo[1]; c1 <= hi[1]; ++c1)
       for (int c2 = lo[2]; c2 <= hi[2]; ++c2) {
         const int id = (c0 * P.ncube[1] + c1) * P.ncube[2] + c2;
+        // the atoms of a residue are neighbours in the array and in space: lanes that hit the same
+        // cube elect one leader for a single atomic (consecutive atoms would otherwise serialise)
+        const unsigned peers = __match_any_sync(__activemask(), id);
+        const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+        const int rank = __popc(peers & ((1u << lane) - 1u));
         if (!FILL) {
-          atomicAdd(&ws.counts[id], 1);
+          if (lane == leader) atomicAdd(&ws.counts[id], __popc(peers));
         } else {
           const int u0 = p[0] - (c0 * P.S - P.pad), u1 = p[1] - (c1 * P.S - P.pad), u2 = p[2] - (c2 * P.S - P.pad);
           const unsigned off = (unsigned)((u0 * P.W + u1) * P.W + u2);
-          const long long pos = (long long)ws.offsets[id] + atomicAdd(&ws.cursor[id], 1);
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&ws.cursor[id], __popc(peers));
+          base = __shfl_sync(peers, base, leader);
+          const long long pos = (long long)ws.offsets[id] + base + rank;
           if (pos < ws.capacity) ws.entries[pos] = (off << 8) | chan;
         }
       }
@@ -215,21 +223,33 @@ af3_scan_kernel(BinWorkspace ws, int n) {
   if (threadIdx.x == 0) ws.offsets[n] = carry;
 }
 
-// grid = B slots.  slot_state[b] = id of the cube whose atoms are currently set in slot b (-1 = clean)
-__global__ void __launch_bounds__(256)
-af3_fill_cubes_kernel(BinWorkspace ws, BinParams P, const int32_t* __restrict__ ijk, float* __restrict__ out,
-                      int64_t out_cube_stride, int32_t* __restrict__ slot_state, int32_t* __restrict__ nonzero) {
-  const int slot = blockIdx.x;
+constexpr int kFillParts = 8;
+
+__device__ __forceinline__ int cube_id_of(const BinParams& P, const int32_t* __restrict__ ijk, int slot) {
+  return ((ijk[3 * slot] / P.S) * P.ncube[1] + ijk[3 * slot + 1] / P.S) * P.ncube[2] + ijk[3 * slot + 2] / P.S;
+}
+
+// grid = (kFillParts, slots).  Slot b currently shows cube ijk_prev[b] (b < n_prev, else it is clean) and
+// is switched to cube ijk_next[b] (b < n_next, else it is left clean).  The CTAs of a slot share its entry
+// lists; each owns the voxels with (offset / 4) % kFillParts == blockIdx.x, so "clear the old cube, then
+// set the new one" stays ordered per voxel inside one CTA while the scattered 4-byte stores of a slot
+// spread over kFillParts CTAs.  Stateless: the caller says what the slots hold.
+__global__ void __launch_bounds__(128)
+af3_fill_cubes_kernel(BinWorkspace ws, BinParams P, const int32_t* __restrict__ ijk_prev, int n_prev,
+                      const int32_t* __restrict__ ijk_next, int n_next, float* __restrict__ out,
+                      int64_t out_cube_stride, int32_t* __restrict__ nonzero) {
+  const int slot = blockIdx.y;
+  const unsigned part = blockIdx.x;
   float* cube = out + (int64_t)slot * out_cube_stride;
   const int64_t W3 = (int64_t)P.W * P.W * P.W;
-  const int prev = slot_state[slot];
-  int next = -1;
-  if (ijk) next = ((ijk[3 * slot] / P.S) * P.ncube[1] + ijk[3 * slot + 1] / P.S) * P.ncube[2] + ijk[3 * slot + 2] / P.S;
+  const int prev = slot < n_prev ? cube_id_of(P, ijk_prev, slot) : -1;
+  const int next = slot < n_next ? cube_id_of(P, ijk_next, slot) : -1;
   if (prev >= 0 && prev != next) {
     const int e0 = ws.offsets[prev], e1 = ws.offsets[prev + 1];
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
       const unsigned v = ws.entries[e];
       const unsigned off = v >> 8, b = v & 7u, r = (v >> 3) & 31u;
+      if (((off >> 2) & (kFillParts - 1)) != part) continue;
       if (b) cube[(int64_t)(b - 1) * W3 + off] = 0.0f;
       if (r) cube[(int64_t)(r + 3) * W3 + off] = 0.0f;
     }
@@ -240,14 +260,13 @@ af3_fill_cubes_kernel(BinWorkspace ws, BinParams P, const int32_t* __restrict__ 
     for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
       const unsigned v = ws.entries[e];
       const unsigned off = v >> 8, b = v & 7u, r = (v >> 3) & 31u;
+      if (((off >> 2) & (kFillParts - 1)) != part) continue;
       if (b) cube[(int64_t)(b - 1) * W3 + off] = 1.0f;
       if (r) cube[(int64_t)(r + 3) * W3 + off] = 1.0f;
     }
   }
-  if (threadIdx.x == 0) {
-    slot_state[slot] = next;
-    if (nonzero) nonzero[slot] = (next >= 0 && ws.offsets[next + 1] > ws.offsets[next]) ? 1 : 0;
-  }
+  if (threadIdx.x == 0 && part == 0 && nonzero && slot < n_next)
+    nonzero[slot] = (ws.offsets[next + 1] > ws.offsets[next]) ? 1 : 0;
 }
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -337,18 +356,21 @@ extern "C" int mica_af3_bin_atoms(const float* xyz, const int8_t* bb_ch, const i
 }
 
 extern "C" int mica_af3_fill_cubes(const void* workspace, int64_t n_atoms, int nz, int ny, int nx, const int perm[3],
-                                   int grid_size, int padding, const int32_t* ijk, int n_slots,
-                                   float* out, int64_t out_cube_stride, int32_t* slot_state, int32_t* nonzero,
-                                   mica_stream_t stream) {
-  MICA_REQUIRE(workspace && out && slot_state, "null pointer");
+                                   int grid_size, int padding, const int32_t* ijk_prev, int n_prev,
+                                   const int32_t* ijk_next, int n_next, float* out, int64_t out_cube_stride,
+                                   int32_t* nonzero, mica_stream_t stream) {
+  MICA_REQUIRE(workspace && out, "null pointer");
+  MICA_REQUIRE(n_prev >= 0 && n_next >= 0 && (ijk_prev || n_prev == 0) && (ijk_next || n_next == 0), "bad slot lists");
   BinParams P;
   int rc = make_bin_params(P, nz, ny, nx, perm, grid_size, padding);
   if (rc) return rc;
+  const int n_slots = n_prev > n_next ? n_prev : n_next;
   if (n_slots <= 0) return MICA_OK;
+  MICA_REQUIRE(n_slots <= 65535, "too many slots");
   const int n_cubes = P.ncube[0] * P.ncube[1] * P.ncube[2];
   BinWorkspace ws = carve(const_cast<void*>(workspace), n_cubes, bin_capacity(n_atoms, grid_size, padding));
-  af3_fill_cubes_kernel<<<n_slots, 256, 0, (cudaStream_t)stream>>>(ws, P, ijk, out, out_cube_stride, slot_state,
-                                                                    nonzero);
+  af3_fill_cubes_kernel<<<dim3(kFillParts, n_slots), 128, 0, (cudaStream_t)stream>>>(
+      ws, P, ijk_prev, n_prev, ijk_next, n_next, out, out_cube_stride, nonzero);
   MICA_LAUNCH_CHECK("af3_fill_cubes_kernel");
   return MICA_OK;
 }

@@ -85,17 +85,32 @@ __device__ __forceinline__ void hist_one(float v, int digit, unsigned p0, unsign
   }
 }
 
-// persistent grid-stride histogram pass; float4 loads when aligned
+// raw float bits whose order-preserving key has `hi` as its top bits (width = number of prefix bits)
+__host__ __device__ __forceinline__ unsigned raw_prefix_of(unsigned hi, int width) {
+  const unsigned top = 1u << (width - 1), mask = (top << 1) - 1u;
+  return (hi & top) ? (hi & (top - 1u)) : (~hi & mask);   // positive floats: drop the set bit; negative: complement
+}
+
+constexpr int kHistReplicas = 4;   // digit-0 pass: per-warp-group copies of the histogram (hot bins contend less)
+
+// persistent grid-stride histogram pass; float4 loads when aligned.
+// Digit 0 counts every element.  Digits 1 and 2 only count the elements inside the one or two prefix
+// buckets found so far -- a fraction of a percent -- so the common case is decided on the RAW bits
+// (two shifts and compares per element); the key transform, nan_to_num and the ballot histogram
+// run only for warps that hold a candidate or a special value (NaN, +-inf, +-0).
 __global__ void __launch_bounds__(512)
 select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
-  __shared__ unsigned h[2 * kBins];
-  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) h[i] = 0;
+  __shared__ unsigned h[kHistReplicas * kBins];
+  for (int i = threadIdx.x; i < kHistReplicas * kBins; i += blockDim.x) h[i] = 0;
   __syncthreads();
   const int round = s->round;
   if (round >= MICA_SELECT_PASSES || s->status != MICA_NORM_PENDING) return;
   const int digit = round_digit(round);
   const unsigned p0 = s->prefix[0], p1 = s->prefix[1];
   const bool same = (p0 == p1);
+  const int shift = digit == 1 ? 21 : 10, width = digit == 1 ? 11 : 22;
+  const unsigned r0 = digit ? raw_prefix_of(p0, width) : 0u, r1 = digit ? raw_prefix_of(p1, width) : 0u;
+  unsigned* h0 = h + (digit == 0 ? ((threadIdx.x >> 5) & (kHistReplicas - 1)) * kBins : 0);
 
   const long long n4 = (((uintptr_t)x & 15) == 0) ? (n >> 2) : 0;
   const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -106,10 +121,20 @@ select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __rest
     bool ok = i < n4;
     float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     if (__ballot_sync(0xffffffffu, ok) == 0xffffffffu) {
-      hist_one(v.x, digit, p0, p1, same, h);
-      hist_one(v.y, digit, p0, p1, same, h);
-      hist_one(v.z, digit, p0, p1, same, h);
-      hist_one(v.w, digit, p0, p1, same, h);
+      if (digit != 0) {
+        const unsigned u[4] = {__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)};
+        bool cand = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const unsigned r = u[c] >> shift, e = u[c] << 1;
+          cand |= (r == r0) | (r == r1) | (e >= 0xff000000u) | (e == 0u);
+        }
+        if (!__any_sync(0xffffffffu, cand)) continue;
+      }
+      hist_one(v.x, digit, p0, p1, same, h0);
+      hist_one(v.y, digit, p0, p1, same, h0);
+      hist_one(v.z, digit, p0, p1, same, h0);
+      hist_one(v.w, digit, p0, p1, same, h0);
     } else if (ok) {  // ragged last warp: plain atomics
       float vv[4] = {v.x, v.y, v.z, v.w};
       for (int c = 0; c < 4; ++c) {
@@ -138,9 +163,18 @@ select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __rest
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) {
-    unsigned c = h[i];
-    if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[0][0]) + i, (unsigned long long)c);
+  if (digit == 0) {
+    for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+      unsigned c = 0;
+#pragma unroll
+      for (int r = 0; r < kHistReplicas; ++r) c += h[r * kBins + i];
+      if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[0][0]) + i, (unsigned long long)c);
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) {
+      unsigned c = h[i];
+      if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[0][0]) + i, (unsigned long long)c);
+    }
   }
 }
 

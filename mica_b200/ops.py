@@ -161,25 +161,29 @@ class Af3CubeFiller:
         self.grid_size, self.padding, self.perm = int(grid_size), int(padding), tuple(perm)
         W = self.grid_size + 2 * self.padding
         self.buffer = torch.zeros((self.n_slots, 24, W, W, W), dtype=torch.float32, device=device)
-        self.slot_state = torch.full((self.n_slots,), -1, dtype=torch.int32, device=device)
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.ws = None
         self._geom = None
-        self._dirty = False
+        self._shown = None          # the ijk tensor whose cubes the slots currently show (kept alive)
 
-    def _fill(self, ijk_ptr, n_slots, nonzero_ptr):
+    def _fill(self, ijk, nonzero_ptr):
         n_atoms, (nz, ny, nx) = self._geom
+        prev = self._shown
         check(lib.mica_af3_fill_cubes(C.c_void_p(self.ws.data_ptr()), n_atoms, nz, ny, nx, _lib.int3(self.perm),
-                                      self.grid_size, self.padding, ijk_ptr, n_slots,
+                                      self.grid_size, self.padding,
+                                      C.c_void_p(prev.data_ptr()) if prev is not None else None,
+                                      int(prev.shape[0]) if prev is not None else 0,
+                                      C.c_void_p(ijk.data_ptr()) if ijk is not None else None,
+                                      int(ijk.shape[0]) if ijk is not None else 0,
                                       C.c_void_p(self.buffer.data_ptr()), self.buffer.stride(0),
-                                      C.c_void_p(self.slot_state.data_ptr()), nonzero_ptr, _stream()),
-              'af3_fill_cubes')
+                                      nonzero_ptr, _stream()), 'af3_fill_cubes')
+        self._shown = ijk
 
     def clear(self):
         """Un-scatter every slot (buffer back to all zeros)."""
-        if self._dirty and self.ws is not None:
-            self._fill(None, self.n_slots, None)
-        self._dirty = False
+        if self._shown is not None and self.ws is not None:
+            self._fill(None, None)
+        self._shown = None
 
     def bin(self, coords, bb_ch, aa_ch, origin_xyz, shape_zyx, clip_hi_xyz=None):
         """Bin the atoms per cube (global cube grid of ``shape_zyx``).  Returns the device
@@ -205,6 +209,11 @@ class Af3CubeFiller:
         self._geom = (n, (nz, ny, nx))
         return self.status
 
+    def share_bins(self, other: 'Af3CubeFiller'):
+        """Use ``other``'s per-cube atom bins (one binning pass serves several slot buffers)."""
+        self.clear()
+        self.ws, self._geom, self.status = other.ws, other._geom, other.status
+
     def fill(self, ijk: torch.Tensor, nonzero: torch.Tensor | None = None) -> torch.Tensor:
         """AF3 channels of the cubes ``ijk`` (int32 [B,3], B <= n_slots) -> view [B,24,W,W,W]."""
         B = int(ijk.shape[0])
@@ -213,8 +222,8 @@ class Af3CubeFiller:
         if self._geom is None:
             raise _lib.MicaError('Af3CubeFiller.fill before bin')
         p_nz = _dev(nonzero, torch.int32, 'nonzero') if nonzero is not None else None
-        self._fill(_dev(ijk, torch.int32, 'ijk'), B, p_nz)
-        self._dirty = True
+        _dev(ijk, torch.int32, 'ijk')
+        self._fill(ijk, p_nz)
         return self.buffer[:B]
 
 

@@ -104,7 +104,7 @@ class MapPipeline:
         self.af3 = None                 # [24,nz,ny,nx] float32, device (None -> zero AF3 features)
         self.stats = None
         self.norm_status = None
-        self._x = self._af = None
+        self._x, self._af, self._nz = [None, None], [None, None], [None, None]
         self.timer = _no_timer      # bench.py swaps in a StageTimer
         #: upper clip bounds for the (x,y,z) atom indices; None = the reference's (nz-1,ny-1,nx-1) quirk (D7)
         self.af3_clip = None
@@ -113,8 +113,13 @@ class MapPipeline:
         if af3_mode not in ('sparse', 'dense'):
             raise MicaError(f'af3_mode must be sparse or dense, got {af3_mode!r}')
         self.af3_mode = af3_mode
-        self._filler = None
+        self._fillers = [None, None]    # one per prefetch buffer
+        self._bins = None               # the filler that holds the per-cube atom bins of the current map
         self._atoms_binned = False
+        #: cut batch n+1 on a side stream while the model and the stitch of batch n run on the
+        #: caller's stream (two input buffers).  False = everything on the caller's stream.
+        self.prefetch = True
+        self._pre_stream = None
 
     # ------------------------------------------------------------------ stage 1+2
     def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
@@ -159,11 +164,17 @@ class MapPipeline:
             raise MicaError('encode_af3 needs the normalised map (its shape and origin)')
         if self.af3_mode == 'sparse':
             perm, _ = self.header.transpose_order()
-            f = self._filler
-            if f is None or f.perm != tuple(perm) or f.n_slots < self.batch_cubes:
-                self._filler = f = ops.Af3CubeFiller(self.device, self.batch_cubes, self.grid_size, self.padding, perm)
+            for i in range(2):
+                f = self._fillers[i]
+                if f is None or f.perm != tuple(perm) or f.n_slots < self.batch_cubes:
+                    self._fillers[i] = ops.Af3CubeFiller(self.device, self.batch_cubes, self.grid_size,
+                                                         self.padding, perm)
+                else:
+                    f.clear()                         # with the OLD bins, before they are rebuilt
+            f = self._fillers[0]
             with self.timer('af3_bin_atoms'):
                 status = f.bin(coords, bb_ch, aa_ch, self.header.origin, self._global_shape(), self.af3_clip)
+            self._fillers[1].share_bins(f)
             self.af3, self._af3_status, self._atoms_binned = None, status, True
             if defer_status:
                 return True
@@ -191,57 +202,100 @@ class MapPipeline:
         self.ijk = torch.from_numpy(self.ijk_host).to(self.device)
         return self.ijk_host
 
-    def _buffers(self, B):
+    def _buffers(self, B, slot=0):
         W = self.window
-        if self._x is None or self._x.shape[0] < B:
-            self._x = torch.empty((B, 1, W, W, W), dtype=torch.float32, device=self.device)
-            self._nz = torch.empty(B, dtype=torch.int32, device=self.device)
-        return self._x[:B], self._nz[:B]
+        if self._x[slot] is None or self._x[slot].shape[0] < B:
+            self._x[slot] = torch.empty((B, 1, W, W, W), dtype=torch.float32, device=self.device)
+            self._nz[slot] = torch.empty(B, dtype=torch.int32, device=self.device)
+        return self._x[slot][:B], self._nz[slot][:B]
 
-    def _af_buffer(self, B):
+    def _af_buffer(self, B, slot=0):
         W = self.window
-        if self._af is None or self._af.shape[0] < B:
-            self._af = torch.empty((B, 24, W, W, W), dtype=torch.float32, device=self.device)
-        return self._af[:B]
+        if self._af[slot] is None or self._af[slot].shape[0] < B:
+            self._af[slot] = torch.empty((B, 24, W, W, W), dtype=torch.float32, device=self.device)
+        return self._af[slot][:B]
 
-    def extract_batch(self, b0: int, b1: int, want_flags: bool = False):
+    def _extract_map(self, ijk, x):
+        ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x)
+
+    def _extract_af3(self, ijk, af, nonzero):
+        ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af, nonzero=nonzero)
+
+    def extract_batch(self, b0: int, b1: int, want_flags: bool = False, slot: int = 0):
         """Cubes [b0,b1) -> (exp_map [B,1,W,W,W], af_features [B,24,W,W,W][, nonzero flags])
-        -- the two tensors MICA.forward takes (models/model.py:331)."""
-        x, nzf = self._buffers(b1 - b0)
+        -- the two tensors MICA.forward takes (models/model.py:331).  ``slot`` picks one of
+        the two input buffers (the prefetch of batch n+1 must not overwrite batch n)."""
+        x, nzf = self._buffers(b1 - b0, slot)
         ijk = self.ijk[b0:b1]
         with self.timer('extract_map'):
-            ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x)
+            self._extract_map(ijk, x)
         if self._atoms_binned:
             with self.timer('af3_fill_cubes'):
-                af = self._filler.fill(ijk, nzf if want_flags else None)
+                af = self._fillers[slot].fill(ijk, nzf if want_flags else None)
         elif self.af3 is not None:
-            af = self._af_buffer(b1 - b0)
+            af = self._af_buffer(b1 - b0, slot)
             with self.timer('extract_af3'):
-                ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
-                                  nonzero=nzf if want_flags else None)
+                self._extract_af3(ijk, af, nzf if want_flags else None)
         else:
-            af = self._af_buffer(b1 - b0)
+            af = self._af_buffer(b1 - b0, slot)
             af.zero_()                                         # dataset/dataset.py:218-219
             if want_flags:
                 nzf.zero_()
         return (x, af, nzf) if want_flags else (x, af)
 
+    def _new_volumes(self):
+        return ops.StitchedVolumes(self.cube_shape, self.device)
+
     # ---------------------------------------------------------------- stage 5 (+model)
     def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None):
         """run_inference + reconstruct_volume (utils/predict.py:307-587) without the
-        per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits."""
+        per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits, enqueued
+        on the current stream.  With ``prefetch`` the cubes of batch n+1 are cut on a side
+        stream while the model and the softmax/argmax + stitch of batch n run."""
         if self.normalized is None:
             raise MicaError('no normalised map')
         self.cube_index()
         if vols is None:
-            vols = ops.StitchedVolumes(self.cube_shape, self.device)
+            vols = self._new_volumes()
         n = len(self.ijk_host)
-        for b0 in range(0, n, self.batch_cubes):
-            b1 = min(n, b0 + self.batch_cubes)
-            x, af = self.extract_batch(b0, b1)
-            bb, ca, aa = model_fn(x, af)
+        batches = [(b0, min(n, b0 + self.batch_cubes)) for b0 in range(0, n, self.batch_cubes)]
+        if not batches:
+            return vols
+        if not self.prefetch or len(batches) == 1:
+            for b0, b1 in batches:
+                x, af = self.extract_batch(b0, b1)
+                bb, ca, aa = model_fn(x, af)
+                with self.timer('postproc_stitch'):
+                    ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+            return vols
+
+        main = torch.cuda.current_stream(self.device)
+        if self._pre_stream is None:
+            self._pre_stream = torch.cuda.Stream(self.device)
+        pre = self._pre_stream
+        pre.wait_stream(main)                    # normalised map, atom bins, ijk are produced on `main`
+        ready, consumed = [None, None], [None, None]
+
+        def cut(i):
+            slot = i & 1
+            with torch.cuda.stream(pre):
+                if consumed[slot] is not None:
+                    pre.wait_event(consumed[slot])           # the model has read this buffer's last batch
+                out = self.extract_batch(*batches[i], slot=slot)
+                ready[slot] = torch.cuda.Event()
+                ready[slot].record(pre)
+            return out
+
+        cur = cut(0)
+        for i, (b0, b1) in enumerate(batches):
+            nxt = cut(i + 1) if i + 1 < len(batches) else None
+            main.wait_event(ready[i & 1])
+            bb, ca, aa = model_fn(*cur)
+            consumed[i & 1] = torch.cuda.Event()
+            consumed[i & 1].record(main)
             with self.timer('postproc_stitch'):
                 ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+            cur = nxt
         return vols
 
     # ------------------------------------------------------------------ whole path

@@ -214,37 +214,14 @@ class SlabPipeline(MapPipeline):
         self.box = ((0, 0, me.out_lo), (self.cube_shape[0], self.cube_shape[1], me.out_hi - me.out_lo))
         return self.ijk_host
 
-    def extract_batch(self, b0, b1, want_flags=False):
-        x, nzf = self._buffers(b1 - b0)
-        ijk = self.ijk[b0:b1]
-        with self.timer('extract_map'):
-            ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x,
-                              global_nz=self.global_nz, z0=self.z0)
-        if self._atoms_binned:
-            with self.timer('af3_fill_cubes'):
-                af = self._filler.fill(ijk, nzf if want_flags else None)
-        elif self.af3 is not None:
-            af = self._af_buffer(b1 - b0)
-            with self.timer('extract_af3'):
-                ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
-                                  global_nz=self.global_nz, z0=self.z0, nonzero=nzf if want_flags else None)
-        else:
-            af = self._af_buffer(b1 - b0)
-            af.zero_()
-            if want_flags:
-                nzf.zero_()
-        return (x, af, nzf) if want_flags else (x, af)
+    def _extract_map(self, ijk, x):
+        ops.extract_cubes(self.normalized, ijk, self.grid_size, self.padding, self.perm, out=x,
+                          global_nz=self.global_nz, z0=self.z0)
 
-    def predict_and_stitch(self, model_fn, vols=None):
-        self.cube_index()
-        if vols is None:
-            org, ext = self.box
-            vols = ops.StitchedVolumes(self.cube_shape, self.device, org=org, ext=ext)
-        n = len(self.ijk_host)
-        for b0 in range(0, n, self.batch_cubes):
-            b1 = min(n, b0 + self.batch_cubes)
-            x, af = self.extract_batch(b0, b1)
-            bb, ca, aa = model_fn(x, af)
-            with self.timer('postproc_stitch'):
-                ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
-        return vols
+    def _extract_af3(self, ijk, af, nonzero):
+        ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af,
+                          global_nz=self.global_nz, z0=self.z0, nonzero=nonzero)
+
+    def _new_volumes(self):
+        org, ext = self.box
+        return ops.StitchedVolumes(self.cube_shape, self.device, org=org, ext=ext)
