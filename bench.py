@@ -277,9 +277,11 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
         ev0.record()
+        t_host = time.perf_counter()
         for _ in range(args.steps):
             vols = pipe.run(src, header, atoms, model_fn, vols)
         ev1.record()
+        t_host = (time.perf_counter() - t_host) / args.steps * 1e3      # host time spent enqueueing one step
         sync()
         ms = ev0.elapsed_time(ev1)
         launches = ops.launch_count() - launches0
@@ -290,10 +292,10 @@ def run_ours(args):
             t = torch.tensor([ms], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms / args.steps, stages, launches, clk, vols
+        return ms / args.steps, stages, launches, clk, vols, t_host
 
     pipe = make_pipe(args.af3_mode)
-    ms_per_step, stages, launches, clk, vols = measure(pipe, True)
+    ms_per_step, stages, launches, clk, vols, host_ms = measure(pipe, True)
     n_vox_rank = int(np.prod(pipe.normalized.shape)) if world == 1 else pipe.owned_voxels
     n_vox = n_vox_rank * world
     value = n_vox / (ms_per_step * 1e-3) / 1e9
@@ -305,7 +307,7 @@ def run_ours(args):
         del vols
         vols = None
         pipe2 = make_pipe(other)
-        ms2, stages2, _, _, vols2 = measure(pipe2, False)
+        ms2, stages2, _, _, vols2, _ = measure(pipe2, False)
         variant = {'af3_mode': other, 'ms_per_step': ms2, 'value': n_vox / (ms2 * 1e-3) / 1e9, 'unit': UNIT,
                    'stage_ms_per_step': {k: round(v[1] / args.steps, 4) for k, v in stages2.items()}}
         del pipe2, vols2
@@ -395,7 +397,7 @@ def run_ours(args):
             'stage_ms_per_step': stage_ms, 'stage_frac_of_peak': stage_frac,
         },
         'af3_mode': args.af3_mode, 'variant': variant,
-        'clocks': clk, 'gpu_launches': int(launches), 'e2e': e2e,
+        'clocks': clk, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'host_loop_enqueue_ms': getattr(pipe, 'last_loop_enqueue_ms', None), 'e2e': e2e,
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_baseline(args)

@@ -107,6 +107,12 @@ int mica_select_result(const void* workspace, float* median, float* p999, int64_
  * when the status is not MICA_NORM_OK. */
 int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* workspace, mica_stream_t stream);
 
+/* test hooks for the normaliser: (1) evaluate the NumPy expression operation by operation for
+ * every voxel instead of the short equivalent path (returns the previous setting); (2) put
+ * given thresholds into a select workspace as if mica_order_stats_f32 had found them. */
+int mica_normalize_force_reference_arith(int on);
+int mica_select_set_thresholds(void* workspace, float median, float p, mica_stream_t stream);
+
 /* ------------------------------------------------------------ R4 AF3 encoder
  * Replaces transform_coordinates + the per-atom loop at
  * utils/preprocessing.py:172-178,275-298 (twin: create_AF3_encodings.py:52-106).

@@ -51,6 +51,8 @@ SIGNATURES = {
     'mica_order_stats_f32': (_i, [_p, _i64, _p, _p]),
     'mica_select_result': (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(_i), _p]),
     'mica_normalize_apply_f32': (_i, [_p, _p, _i64, _p, _p]),
+    'mica_normalize_force_reference_arith': (_i, [_i]),
+    'mica_select_set_thresholds': (_i, [_p, _f, _f, _p]),
     'mica_af3_encode': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     'mica_af3_bins_workspace_bytes': (_sz, [_i64, _i, _i, _i, C.POINTER(_i), _i, _i]),
     'mica_af3_bin_atoms': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i,

@@ -20,6 +20,19 @@ int check_cuda(cudaError_t e, const char* what) {
   int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? MICA_ERR_NO_DEVICE : MICA_ERR_CUDA;
   return set_error(code, "%s: %s", what, cudaGetErrorString(e));
 }
+TensorMapEncodeFn tensor_map_encode_fn() {
+  static TensorMapEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (TensorMapEncodeFn)p;
+  }
+  return fn;
+}
 }  // namespace mica
 
 extern "C" {

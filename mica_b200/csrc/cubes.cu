@@ -229,24 +229,6 @@ extract_tma_kernel(const __grid_constant__ CUtensorMap tmap, TmaExtractParams P)
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 constexpr int kTmaBT = 4;  // b-rows per tile: 4 * 64 * 128 B = 32 KB of shared memory per CTA
 
 __global__ void init_flags_kernel(int32_t* nonzero, float* cube_max, int n) {
@@ -312,7 +294,7 @@ extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_c
   const size_t tma_smem = (size_t)kTmaBT * W * 128 + 1024;
   if (contiguous_axis == 0 && W % 32 == 0 && W <= 256 && nx % 4 == 0 && chan_stride % 4 == 0 &&
       ((uintptr_t)vol & 15) == 0 && !getenv("MICA_NO_TMA")) {
-    EncodeTiledFn enc = encode_tiled_fn();
+    TensorMapEncodeFn enc = tensor_map_encode_fn();
     if (enc) {
       const int local[3] = {nz_local, ny, nx};
       // dims: (x, axis walked by c, axis walked by b, channel)
@@ -322,7 +304,7 @@ extern "C" int mica_extract_cubes(const float* vol, int64_t chan_stride, int n_c
                             (cuuint64_t)(n_channels > 1 ? chan_stride : (int64_t)nz_local * ny * nx) * 4};
       cuuint32_t box[4] = {32, (cuuint32_t)W, (cuuint32_t)kTmaBT, 1};
       cuuint32_t estr[4] = {1, 1, 1, 1};
-      CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+      CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_64B;   // measured best of the four on B200
       if (const char* e = getenv("MICA_TMA_L2PROMO")) {   // experiment knob: 0 none, 1 64B, 2 128B, 3 256B
         const int v = atoi(e);
         promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B

@@ -25,6 +25,9 @@
 //   prefilter_cols / prefilter_rows / gather3 / gather1
 //                        general fall-backs (short or very long lines, strong down-sampling,
 //                        trilinear): one thread per line / one thread per output voxel
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mica {
@@ -483,6 +486,177 @@ march3_kernel(const double* __restrict__ c, int sy, int sx, const ZWin* __restri
   }
 }
 
+// ------------------------------------------------- marching gather, TMA-fed
+// Same march as march3_kernel, but the source rows of each plane arrive as one
+// cp.async.bulk.tensor box ([ROWS y] x [XB x] float64 of the coefficient volume, tensor map
+// dims (x, y, z)) in a kStages-deep shared-memory ring filled by one elected thread: the loads
+// of planes p+1..p+3 are in flight while plane p is interpolated, and no register is spent on
+// staging.  Rows / columns past the map edge are zero-filled by the TMA unit and never tapped.
+constexpr int kMarchStages = 6;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  }
+}
+
+// grid = (ceil(nx / 64), ceil(ny / 8), z chunks), block = 256; dynamic smem = ring + 1 KB alignment slack
+template <int NI>
+__global__ void __launch_bounds__(256, 3)
+march3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int xb, const ZWin* __restrict__ zw,
+                  const Tap* __restrict__ ty, const Tap* __restrict__ tx, float* __restrict__ dst, int ny, int nx,
+                  int nz_local, int zchunk) {
+  constexpr int TX = 64, TY = 8, ROWS = NI * 4;
+  extern __shared__ uint8_t march_smem[];
+  __shared__ double A[2][ROWS][TX];
+  __shared__ __align__(8) uint64_t full[kMarchStages];
+  __shared__ int s_lo[2];
+  double* ring = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(march_smem) + 127) & ~(uintptr_t)127);
+  const int t = threadIdx.x;
+  const int lx = t & (TX - 1), lr = t >> 6;
+  const int x0 = blockIdx.x * TX, x = x0 + lx;
+  const int y0 = blockIdx.y * TY;
+  const int z_begin = blockIdx.z * zchunk, z_end = min(nz_local, z_begin + zchunk);
+  if (z_begin >= z_end) return;
+  const int stage_elems = ROWS * xb;
+  const int stage_stride = (stage_elems + 15) & ~15;   // ring stages stay 128-byte aligned (TMA destination)
+
+  if (t == 0) {
+    s_lo[0] = s_lo[1] = 0x7fffffff;
+    for (int i = 0; i < kMarchStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // lowest source row / column any output of this tile taps (zero-weight taps, D11, excluded)
+  if (t < TY * 4) {
+    const int r = min(y0 + (t >> 2), ny - 1);
+    if (ty[r].w[t & 3] != 0.0) atomicMin(&s_lo[0], ty[r].idx[t & 3]);
+  }
+  {
+    const int xx = min(x, nx - 1);
+#pragma unroll
+    for (int l = 0; l < 4; ++l)
+      if (tx[xx].w[l] != 0.0) atomicMin(&s_lo[1], tx[xx].idx[l]);
+  }
+  __syncthreads();
+  const int lo_y = (s_lo[0] == 0x7fffffff) ? 0 : s_lo[0];
+  // even: the box must start on a 16-byte boundary of the float64 rows (odd starts fault on B200)
+  const int lo_x = ((s_lo[1] == 0x7fffffff) ? 0 : s_lo[1]) & ~1;
+
+  // everything below addresses shared memory with precomputed 32-bit byte offsets (one add per
+  // access): the inner loop is issue-bound, and generic 64-bit index arithmetic had tripled it
+  double wx[4];
+  uint32_t r_off[NI][4];   // byte offset of tap l of staged row lr + 4 i inside a ring stage
+  {
+    const Tap T = tx[min(x, nx - 1)];
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      wx[l] = T.w[l];
+      const int ixl = (T.w[l] != 0.0) ? min(xb - 1, T.idx[l] - lo_x) : 0;
+#pragma unroll
+      for (int i = 0; i < NI; ++i) r_off[i][l] = (uint32_t)(((lr + 4 * i) * xb + ixl) * 8);
+    }
+  }
+  double wy[2][4];
+  uint32_t a_rd[2][4];     // byte offset of y tap m of output o inside A[0]
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const Tap T = ty[min(y0 + lr + 4 * o, ny - 1)];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      wy[o][m] = T.w[m];
+      const int iym = (T.w[m] != 0.0) ? min(ROWS - 1, T.idx[m] - lo_y) : 0;
+      a_rd[o][m] = (uint32_t)((iym * TX + lx) * 8);
+    }
+  }
+  const uint32_t a_base = smem_addr(&A[0][0][0]), ring_base = smem_addr(ring);
+  const uint32_t a_wr = a_base + (uint32_t)((lr * TX + lx) * 8);      // + i * 4 rows, + buffer
+  constexpr uint32_t kABuf = ROWS * TX * 8, kARow4 = 4 * TX * 8;
+  double v[2][4];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[o][m] = 0.0;
+
+  const int p_start = zw[z_begin].base, p_last = zw[z_end - 1].base + 3;
+  const uint32_t stage_bytes = (uint32_t)stage_elems * 8u;
+  auto issue = [&](int p, int sidx) {
+    const uint32_t bar = smem_addr(&full[sidx]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(stage_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(ring_base + (uint32_t)sidx * (uint32_t)stage_stride * 8u), "l"(&tmap), "r"(lo_x), "r"(lo_y), "r"(p), "r"(bar)
+        : "memory");
+  };
+  if (t == 0)
+    for (int i = 0; i < kMarchStages && p_start + i <= p_last; ++i) issue(p_start + i, i);
+
+  auto lds = [](uint32_t addr) {
+    double d;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(d) : "r"(addr));
+    return d;
+  };
+  // running output pointers (advance one plane per emitted z)
+  const int64_t out_plane = (int64_t)ny * nx;
+  float* outp[2];
+  bool outok[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int y = y0 + lr + 4 * o;
+    outok[o] = x < nx && y < ny;
+    outp[o] = dst + ((int64_t)z_begin * ny + min(y, ny - 1)) * nx + min(x, nx - 1);
+  }
+
+  int zc = z_begin;
+  int next_emit = zw[zc].base + 3;
+  int sidx = 0;
+  uint32_t phase = 0, abuf = 0;
+  for (int p = p_start; p <= p_last; ++p) {
+    mbar_wait(smem_addr(&full[sidx]), phase);
+    const uint32_t raw = ring_base + (uint32_t)sidx * (uint32_t)stage_stride * 8u;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const double xi = wx[0] * lds(raw + r_off[i][0]) + wx[1] * lds(raw + r_off[i][1]) +
+                        wx[2] * lds(raw + r_off[i][2]) + wx[3] * lds(raw + r_off[i][3]);
+      asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_wr + abuf + i * kARow4), "d"(xi) : "memory");
+    }
+    __syncthreads();   // A[abuf] complete; every thread is done with ring stage sidx
+    if (t == 0 && p + kMarchStages <= p_last) issue(p + kMarchStages, sidx);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const uint32_t ab = a_base + abuf;
+      const double vn = wy[o][0] * lds(ab + a_rd[o][0]) + wy[o][1] * lds(ab + a_rd[o][1]) +
+                        wy[o][2] * lds(ab + a_rd[o][2]) + wy[o][3] * lds(ab + a_rd[o][3]);
+      v[o][0] = v[o][1];
+      v[o][1] = v[o][2];
+      v[o][2] = v[o][3];
+      v[o][3] = vn;
+    }
+    while (zc < z_end && next_emit <= p) {
+      const ZWin Wz = zw[zc];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const double acc = Wz.w[0] * v[o][0] + Wz.w[1] * v[o][1] + Wz.w[2] * v[o][2] + Wz.w[3] * v[o][3];
+        if (outok[o]) st_stream(outp[o], (float)acc);
+        outp[o] += out_plane;
+      }
+      ++zc;
+      if (zc < z_end) next_emit = zw[zc].base + 3;
+    }
+    abuf ^= kABuf;
+    if (++sidx == kMarchStages) {
+      sidx = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 gather1_kernel(const float* __restrict__ src, int sy, int sx, const Tap* __restrict__ tz,
                const Tap* __restrict__ ty, const Tap* __restrict__ tx, float* __restrict__ dst, int ny,
@@ -643,11 +817,41 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
       const int zchunk = (dst_nz_local + nzc - 1) / nzc;
       dim3 mgrid(xt, yt, (dst_nz_local + zchunk - 1) / zchunk);
       MICA_REQUIRE(yt <= 65535 && mgrid.z <= 65535, "output too large for the launch grid");
-      if (span_y <= 12)
-        march3_kernel<3><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
-      else
-        march3_kernel<4><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
-      MICA_LAUNCH_CHECK("march3_kernel");
+      // TMA-fed ring when the coefficient rows are 16-byte multiples and the x span of a 64-wide
+      // output tile fits one box; else the register-prefetch variant
+      const double zoom_x = nx > 1 ? (double)(sx - 1) / (double)(nx - 1) : 1.0;
+      const int xb = (((int)floor(63.0 * zoom_x) + 5) + 1 + 1) & ~1;   // span + 1 (even box start), even width
+      const int rows = span_y <= 12 ? 12 : 16;
+      bool tma_ok = false;
+      CUtensorMap tmap;
+      if (sx % 2 == 0 && xb <= 256 && !getenv("MICA_NO_TMA")) {
+        if (TensorMapEncodeFn enc = tensor_map_encode_fn()) {
+          cuuint64_t gdim[3] = {(cuuint64_t)sx, (cuuint64_t)sy, (cuuint64_t)src_nz_local};
+          cuuint64_t gstr[2] = {(cuuint64_t)sx * 8, (cuuint64_t)plane * 8};
+          cuuint32_t box[3] = {(cuuint32_t)xb, (cuuint32_t)rows, 1};
+          cuuint32_t estr[3] = {1, 1, 1};
+          tma_ok = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)coeff, gdim, gstr, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+      }
+      if (tma_ok) {
+        const size_t smem = (size_t)kMarchStages * (((size_t)rows * xb + 15) / 16 * 16) * 8 + 128;
+        if (rows == 12) {
+          MICA_CUDA(cudaFuncSetAttribute(march3_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          march3_tma_kernel<3><<<mgrid, 256, smem, st>>>(tmap, xb, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+        } else {
+          MICA_CUDA(cudaFuncSetAttribute(march3_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          march3_tma_kernel<4><<<mgrid, 256, smem, st>>>(tmap, xb, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+        }
+        MICA_LAUNCH_CHECK("march3_tma_kernel");
+      } else {
+        if (span_y <= 12)
+          march3_kernel<3><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+        else
+          march3_kernel<4><<<mgrid, 256, 0, st>>>(coeff, sy, sx, zw, ty, tx, dst, ny, nx, dst_nz_local, zchunk);
+        MICA_LAUNCH_CHECK("march3_kernel");
+      }
     } else {
       gather3_kernel<<<grid, 128, 0, st>>>(coeff, sy, sx, tz, ty, tx, dst, ny, nx);
       MICA_LAUNCH_CHECK("gather3_kernel");

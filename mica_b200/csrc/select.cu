@@ -343,11 +343,37 @@ __device__ __forceinline__ float normalize_one(float x, float med, float p) {
   return __fdiv_rn(r, p);
 }
 
+// The same value with a handful of instructions for ordinary inputs.  Walking the NumPy expression:
+//   v <= med            -> m = 0 * (v - med) = +-0, r = +-0 + 0 = +0, y = +0
+//   v - med >= p        -> r = 0 * m + p = p, y = p / p = 1
+//   0 < v - med < p     -> r = m, y = RN(m / p): q0 = RN(m * RN(1/p)), rem = m - q0 * p (exact in an
+//                          fma), y = RN(q0 + rem * RN(1/p)) is the correctly rounded quotient
+//                          (Markstein's division-by-reciprocal step) as long as nothing underflows.
+// Huge / non-finite inputs (v - med could overflow, nan_to_num applies), quotients near the
+// denormal range and a divisor whose significand is all ones take normalize_one().
+__device__ __forceinline__ float normalize_fast(float x, float med, float p, float rcp, bool rcp_ok) {
+  const unsigned a = __float_as_uint(x) & 0x7fffffffu;
+  if (a >= 0x7e000000u || !rcp_ok) return normalize_one(x, med, p);
+  if (!(x > med)) return 0.0f;
+  const float d = __fsub_rn(x, med);
+  if (d >= p) return 1.0f;
+  const float q0 = __fmul_rn(d, rcp);
+  if (q0 < 1e-30f) return __fdiv_rn(d, p);
+  const float rem = __fmaf_rn(-q0, p, d);
+  return __fmaf_rn(rem, rcp, q0);
+}
+
+template <bool FAST>
 __global__ void __launch_bounds__(256)
 normalize_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long long n,
                        const SelectState* __restrict__ s) {
   if (s->status != MICA_NORM_OK) return;
   const float med = s->median, p = s->p;
+  const float rcp = __fdiv_rn(1.0f, p);
+  // the reciprocal step needs finite, normal operands and a divisor that is not 2 - ulp
+  const unsigned pu = __float_as_uint(p), ru = __float_as_uint(rcp);
+  const bool rcp_ok = FAST && p > 1e-30f && p < 1e30f && (pu & 0x7fffffu) != 0x7fffffu && (ru & 0x7f800000u) != 0u &&
+                      fabsf(med) < 1e30f;
   const bool vec = ((((uintptr_t)x) | ((uintptr_t)y)) & 15) == 0;
   const long long n4 = vec ? (n >> 2) : 0;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -356,13 +382,13 @@ normalize_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long 
   float4* y4 = reinterpret_cast<float4*>(y);
   for (long long i = tid; i < n4; i += stride) {
     float4 v = x4[i];
-    v.x = normalize_one(v.x, med, p);
-    v.y = normalize_one(v.y, med, p);
-    v.z = normalize_one(v.z, med, p);
-    v.w = normalize_one(v.w, med, p);
+    v.x = normalize_fast(v.x, med, p, rcp, rcp_ok);
+    v.y = normalize_fast(v.y, med, p, rcp, rcp_ok);
+    v.z = normalize_fast(v.z, med, p, rcp, rcp_ok);
+    v.w = normalize_fast(v.w, med, p, rcp, rcp_ok);
     y4[i] = v;
   }
-  for (long long i = n4 * 4 + tid; i < n; i += stride) y[i] = normalize_one(x[i], med, p);
+  for (long long i = n4 * 4 + tid; i < n; i += stride) y[i] = normalize_fast(x[i], med, p, rcp, rcp_ok);
 }
 
 }  // namespace mica
@@ -433,12 +459,39 @@ extern "C" int mica_select_result(const void* workspace, float* median, float* p
   return MICA_OK;
 }
 
+static int g_normalize_reference_arith = 0;
+
+// test hook: on != 0 evaluates the NumPy expression operation by operation for every voxel
+// (normalize_one) instead of the short equivalent path; returns the previous setting
+extern "C" int mica_normalize_force_reference_arith(int on) {
+  const int was = g_normalize_reference_arith;
+  g_normalize_reference_arith = on ? 1 : 0;
+  return was;
+}
+
+// test hook: stores median / percentile into a select workspace as if mica_order_stats_f32 had found them
+__global__ void select_set_thresholds_kernel(SelectState* s, float median, float p) {
+  s->median = median;
+  s->p = p;
+  s->status = MICA_NORM_OK;
+  s->round = MICA_SELECT_PASSES;
+}
+extern "C" int mica_select_set_thresholds(void* workspace, float median, float p, mica_stream_t stream) {
+  MICA_REQUIRE(workspace, "null workspace");
+  select_set_thresholds_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_of(workspace), median, p);
+  MICA_LAUNCH_CHECK("select_set_thresholds_kernel");
+  return MICA_OK;
+}
+
 extern "C" int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* workspace, mica_stream_t stream) {
   MICA_REQUIRE(x && y && workspace, "null pointer");
   if (n <= 0) return MICA_OK;
   int64_t want = ceil_div64(ceil_div64(n, 4), 256);
   int grid = (int)(want < (int64_t)kNumSMs * 8 ? want : (int64_t)kNumSMs * 8);
-  normalize_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n, state_of(workspace));
+  if (g_normalize_reference_arith)
+    normalize_apply_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n, state_of(workspace));
+  else
+    normalize_apply_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, n, state_of(workspace));
   MICA_LAUNCH_CHECK("normalize_apply_kernel");
   return MICA_OK;
 }

@@ -12,6 +12,7 @@ preprocessing.py, create_grids.py, predict.py) are thin shells over this class.
 """
 from __future__ import annotations
 
+import time
 from contextlib import contextmanager
 from dataclasses import dataclass
 
@@ -269,6 +270,7 @@ class MapPipeline:
                     ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
             return vols
 
+        t_enqueue = time.perf_counter()
         main = torch.cuda.current_stream(self.device)
         if self._pre_stream is None:
             self._pre_stream = torch.cuda.Stream(self.device)
@@ -296,6 +298,7 @@ class MapPipeline:
             with self.timer('postproc_stitch'):
                 ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
             cur = nxt
+        self.last_loop_enqueue_ms = (time.perf_counter() - t_enqueue) * 1e3     # host side of the batch loop
         return vols
 
     # ------------------------------------------------------------------ whole path

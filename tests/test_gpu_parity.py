@@ -133,6 +133,44 @@ def test_normalize_bit_exact_sizes(cuda, n):
     _check_normalize(x.reshape(-1, 1, 1) if n < 8 else x, cuda)
 
 
+def test_normalize_short_path_is_bit_identical_to_numpy_arithmetic(cuda):
+    """The lean normaliser (compare / subtract / reciprocal-step division) must give the same
+    float32 bits as the operation-by-operation NumPy expression, for every voxel."""
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    n = 1 << 24
+    st = ops.OrderStats(cuda)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    cases = [(0.0173, 0.91), (-3.5e-3, 7.7e-4), (1.25, 33.333), (0.0, 1.0), (2.5e-5, 1.9999999),
+             (1e-3, float(np.float32(1.9999999) - np.float32(1e-7))), (0.1, 3e-38), (-7.0, 1.17e-36)]
+    for med, p in cases:
+        med, p = np.float32(med), np.float32(p)
+        x = (rng.standard_normal(n) * 3 * float(p) + float(med)).astype(np.float32)
+        x[::97] = med
+        x[1::193] = med + p                      # lands on / next to the clip threshold
+        x[2::389] = np.nextafter(med, np.float32(np.inf))
+        x[3::1021] = np.float32(3e38) * np.sign(x[3::1021])
+        x[4::4099] = np.nan
+        x[5::8191] = np.inf
+        x[6::8191] = -np.inf
+        x[7::997] = np.float32(-0.0)
+        dx = dev(x, cuda)
+        _lib.check(_lib.lib.mica_select_set_thresholds(st._p, float(med), float(p), stream))
+        fast = st.apply(dx).cpu().numpy()
+        was = _lib.lib.mica_normalize_force_reference_arith(1)
+        try:
+            ref = st.apply(dx).cpu().numpy()
+        finally:
+            _lib.lib.mica_normalize_force_reference_arith(was)
+        assert np.array_equal(fast.view(np.uint32), ref.view(np.uint32)), (med, p)
+        # and the operation-by-operation path is NumPy's result (utils/preprocessing.py:122-133)
+        with np.errstate(all='ignore'):
+            v = np.nan_to_num(x[:1 << 20])
+            m = (v > med) * (v - med)
+            want = ((m < p) * m + (m >= p) * p) / p
+        assert np.array_equal(ref[:1 << 20].view(np.uint32), want.astype(np.float32).view(np.uint32)), (med, p)
+
+
 def test_normalize_bit_exact_on_oracle_resampled(cuda, golden_dir):
     """Stage isolation: feed SciPy's own float32 volume to the GPU normaliser."""
     g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
