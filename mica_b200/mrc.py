@@ -53,12 +53,15 @@ def read_mrc(path) -> MrcMap:
                   nxstart=int(w[4]), nystart=int(w[5]), nzstart=int(w[6]))
 
 
-def write_mrc(path, m: MrcMap):
-    data = np.ascontiguousarray(m.data, dtype='<f4')
+def write_mrc(path, m: MrcMap, dtype=np.float32):
+    """``dtype``: float32 (mode 2, what every reference writer produces) or one of the other
+    MRC2014 sample types (int8 / int16 / uint16 / float16), e.g. for label masks."""
+    mode = {np.dtype(v): k for k, v in _MODES.items()}[np.dtype(dtype)]
+    data = np.ascontiguousarray(m.data, dtype=np.dtype(dtype).newbyteorder('<'))
     nz, ny, nx = data.shape
     hdr = np.zeros(256, dtype='<i4')
     fl = hdr.view('<f4')
-    hdr[0:4] = (nx, ny, nz, 2)
+    hdr[0:4] = (nx, ny, nz, mode)
     hdr[4:7] = (m.nxstart, m.nystart, m.nzstart)
     hdr[7:10] = (nx, ny, nz)
     vx, vy, vz = (np.float32(v) for v in m.voxel_size)

@@ -142,6 +142,37 @@ def golden_cubes():
     _save('cubes.npz', **out)
 
 
+def golden_training_twins():
+    """R1/R2/R4 training twins (scripts_for_training_data/create_normalized_map.py,
+    create_AF3_encodings.py): same arithmetic as the inference entry points -- asserted here
+    against the reference's own DataPreprocessor -- stored with the text PDB they parsed."""
+    with tempfile.TemporaryDirectory() as td:
+        src = synthetic.synthetic_map((22, 26, 20), voxel=1.15, seed=17)
+        voxel = (np.float32(1.15),) * 3
+        origin = (np.float32(-4.5), np.float32(3.25), np.float32(8.0))
+        norm_tw, tw_path = rh.training_map_processor(src, voxel, td, origin_xyz=origin)
+        norm_inf, _, _ = rh.resample_and_normalize(src, voxel, os.path.join(td, 'inf'), origin_xyz=origin)
+        assert norm_tw is not None and np.array_equal(norm_tw, norm_inf), 'training twin != inference path'
+        o_norm, _, _ = orc.normalize(orc.resample(src, voxel))
+        assert np.array_equal(o_norm, norm_tw), 'oracle != MapProcessor'
+        # cubic working grid for the encoder (the clip quirk is exercised by preprocess_small)
+        cube = np.abs(synthetic.synthetic_map((20, 20, 20), voxel=1.0, seed=4))
+        norm_c, c_path = rh.training_map_processor(cube, (1.0, 1.0, 1.0), os.path.join(td), origin_xyz=origin)
+        st = synthetic.synthetic_structure(40, (20, 20, 20), seed=9, origin_xyz=origin, margin=0.5,
+                                           hetero_every=7, unknown_every=5)
+        pdb_path = os.path.join(td, 'x_af3_docked.pdb')
+        synthetic.write_pdb(pdb_path, st)
+        enc, names = rh.training_features_encoder(c_path, pdb_path)
+        from mica_b200.pdb import CHANNEL_NAMES, read_pdb_atoms
+        assert list(names) == list(CHANNEL_NAMES)
+        coords, bb, aa, _ = read_pdb_atoms(pdb_path)
+        o_enc, ok = orc.af3_encode(coords, bb, aa, origin, (20, 20, 20))
+        assert ok and np.array_equal(o_enc, enc), 'oracle != FeaturesEncoder'
+        pdb_text = open(pdb_path).read()
+    _save('training_twins.npz', src=src, voxel=np.array(voxel), origin=np.array(origin), normalized=norm_tw,
+          enc_map=norm_c, enc_nonzero=np.argwhere(enc > 0).astype(np.int32), pdb_text=np.array(pdb_text))
+
+
 def golden_stitch():
     """R6-R8: (52,20,12)-voxel map -> 2 cubes -> replayed logits -> 4 volumes,
     through CryoEMTestDataset + run_inference + reconstruct_volume on CPU."""
@@ -176,7 +207,7 @@ def golden_stitch():
 def main():
     assert rh.available(), 'needs /root/reference'
     os.makedirs(GOLDEN, exist_ok=True)
-    for fn in (golden_preprocess, golden_af3_cubic, golden_cubes, golden_stitch):
+    for fn in (golden_preprocess, golden_af3_cubic, golden_cubes, golden_training_twins, golden_stitch):
         print(fn.__name__)
         fn()
 

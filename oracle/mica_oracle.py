@@ -224,27 +224,39 @@ def channel_codes(atom_names, res_names):
     return bb, aa
 
 
-def af3_encode(coords, bb_ch, aa_ch, origin_xyz, shape, dtype=np.float32):
-    """utils/preprocessing.py:268-298 for atoms already filtered to standard
-    residues (``residue.id[0] == ' '``).  ``coords`` float32 [A,3] (x,y,z),
-    ``origin_xyz`` three np.float32.  Returns (volume [24,nz,ny,nx], ok) where
-    ok=False reproduces the IndexError -> ``return False`` path (:344-347)."""
+def af3_indices(coords, bb_ch, aa_ch, origin_xyz, shape):
+    """The voxels utils/preprocessing.py:275-298 sets to 1, as sorted unique linear indices into
+    the C-ordered [24,nz,ny,nx] volume (or None on the IndexError path, :344-347).  Same index
+    arithmetic as the loop; lets full-size grids be checked without the dense float64 volume."""
     coords = np.asarray(coords, dtype=np.float32)
-    vol = np.zeros((24,) + tuple(shape), dtype=dtype)
     origin = np.array([np.float32(o) for o in origin_xyz], dtype=np.float32)
     # float32 - float32 stays float32 (Bio.PDB coords are float32; the reference's
     # np.array((origin.x, origin.y, origin.z)) of np.float32 scalars is float32)
     idx = np.round(coords - origin[None, :]).astype(int)
     idx = np.clip(idx, 0, np.array(shape)[None, :] - 1)
-    nz, ny, nx = shape
+    nz, ny, nx = (int(v) for v in shape)
     # numpy negative indices cannot occur after the clip at 0; overflow raises
     bad = (idx[:, 2] >= nz) | (idx[:, 1] >= ny) | (idx[:, 0] >= nx)
     if bad.any():
+        return None
+    lin = (idx[:, 2].astype(np.int64) * ny + idx[:, 1]) * nx + idx[:, 0]
+    n = np.int64(nz) * ny * nx
+    bb_ch, aa_ch = np.asarray(bb_ch), np.asarray(aa_ch)
+    parts = [bb_ch[bb_ch >= 0].astype(np.int64) * n + lin[bb_ch >= 0],
+             aa_ch[aa_ch >= 0].astype(np.int64) * n + lin[aa_ch >= 0]]
+    return np.unique(np.concatenate(parts))
+
+
+def af3_encode(coords, bb_ch, aa_ch, origin_xyz, shape, dtype=np.float32):
+    """utils/preprocessing.py:268-298 for atoms already filtered to standard
+    residues (``residue.id[0] == ' '``).  ``coords`` float32 [A,3] (x,y,z),
+    ``origin_xyz`` three np.float32.  Returns (volume [24,nz,ny,nx], ok) where
+    ok=False reproduces the IndexError -> ``return False`` path (:344-347)."""
+    vol = np.zeros((24,) + tuple(shape), dtype=dtype)
+    lin = af3_indices(coords, bb_ch, aa_ch, origin_xyz, shape)
+    if lin is None:
         return vol, False
-    sel = bb_ch >= 0
-    vol[bb_ch[sel], idx[sel, 2], idx[sel, 1], idx[sel, 0]] = 1.0
-    sel = aa_ch >= 0
-    vol[aa_ch[sel], idx[sel, 2], idx[sel, 1], idx[sel, 0]] = 1.0
+    vol.reshape(-1)[lin] = 1.0
     return vol, True
 
 

@@ -131,6 +131,32 @@ def training_grids_from_mrc(mrc_path, outdir, grid_size=48, padding=8):
     return count, cubes
 
 
+def training_map_processor(src, voxel_xyz, workdir, origin_xyz=(0, 0, 0)):
+    """scripts_for_training_data/create_normalized_map.py::MapProcessor.process_map.
+    Returns the normalised volume read back from the MRC it wrote (None if it wrote none)."""
+    _setup_path()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'scripts_for_training_data'))
+    import create_normalized_map as m
+    inp = os.path.join(workdir, 'emd_0000.map')
+    out = os.path.join(workdir, 'tw_resampled_normalized_map.mrc')
+    _write_mrc(inp, src, voxel_xyz, origin_xyz)
+    with _quiet():
+        m.MapProcessor(inp).process_map(out, target_voxel_size=1.0)
+    return (_read_mrc(out), out) if os.path.exists(out) else (None, None)
+
+
+def training_features_encoder(normalized_map_path, pdb_path):
+    """scripts_for_training_data/create_AF3_encodings.py::FeaturesEncoder.encode_structure.
+    Returns the float32 (24,nz,ny,nx) volume; IndexError propagates as in the reference."""
+    _setup_path()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'scripts_for_training_data'))
+    import create_AF3_encodings as m
+    with _quiet():
+        enc = m.FeaturesEncoder(normalized_map_path)
+        vol = enc.encode_structure(pdb_path)
+    return vol.astype(np.float32), enc.get_channel_names()
+
+
 class _ReplayModel:
     """Stands where MICA stands in run_inference (utils/predict.py:339): returns
     pre-generated logits for the cubes of the batch, keyed by the map cube's

@@ -111,3 +111,17 @@ def test_oracle_against_live_reference(tmp_path):
     assert n == len(oc) and shp == tuple(oshp)
     for c, m in zip(oc, om):
         assert np.array_equal(cubes[tuple(m[:3])][0], c)
+
+
+def test_training_twins_match_reference_golden(golden_dir, tmp_path):
+    """scripts_for_training_data/create_normalized_map.py + create_AF3_encodings.py outputs
+    (produced by the unmodified reference, oracle/make_golden.py::golden_training_twins)."""
+    from mica_b200.pdb import read_pdb_atoms
+    g = np.load(os.path.join(golden_dir, 'training_twins.npz'))
+    norm, _, _ = orc.normalize(orc.resample(g['src'], g['voxel']))
+    assert np.array_equal(norm, g['normalized'])
+    pdb_path = tmp_path / 'x_af3_docked.pdb'
+    pdb_path.write_text(str(g['pdb_text']))
+    coords, bb, aa, _ = read_pdb_atoms(str(pdb_path))
+    vol, ok = orc.af3_encode(coords, bb, aa, g['origin'], g['enc_map'].shape)
+    assert ok and np.array_equal(np.argwhere(vol > 0).astype(np.int32), g['enc_nonzero'])
