@@ -185,7 +185,6 @@ prefilter_rows(double* __restrict__ data, int n, int64_t n_rows) {
 // before index 0 / after n-1 being the mirror images SciPy's boundary rule implies) has
 // forgotten its start to below double rounding when it reaches the segment.
 constexpr int kHorizon = 30;
-constexpr int kSegs = 8;            // segments per line = 256 threads / 32 lines
 constexpr int kMinSegLine = 96;     // shorter lines take the one-thread-per-line kernels
 
 // Filters samples [k0, k1) of one line in place; all threads of the block call this together
@@ -240,41 +239,43 @@ __device__ __forceinline__ void iir_segment(double* line, int n, int stride, int
   }
 }
 
-// lines along a strided axis.  grid = (ceil(n_cols / 32), n_outer), block = 256, tile [n][32]
-template <typename TIn>
+// lines along a strided axis.  grid = (ceil(n_cols / L), n_outer), block = 256, tile [n][L],
+// 256 / L segments per line
+template <typename TIn, int L>
 __global__ void __launch_bounds__(256)
 prefilter_cols_seg(const TIn* __restrict__ in, double* __restrict__ out, int n, int64_t line_stride,
                    int n_cols, int64_t outer_stride) {
   extern __shared__ double tile[];
-  constexpr int CW = 32;
-  const int col0 = blockIdx.x * CW;
+  constexpr int kSegs = 256 / L;
+  const int col0 = blockIdx.x * L;
   const int64_t base = (int64_t)blockIdx.y * outer_stride + col0;
-  const int ncol = min(CW, n_cols - col0);
-  const int j = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int ncol = min(L, n_cols - col0);
+  const int j = threadIdx.x & (L - 1), seg = threadIdx.x / L;
   for (int k = seg; k < n; k += kSegs)
-    if (j < ncol) tile[k * CW + j] = (double)in[base + (int64_t)k * line_stride + j] * kGain;
+    if (j < ncol) tile[k * L + j] = (double)in[base + (int64_t)k * line_stride + j] * kGain;
   __syncthreads();
   const int len = (n + kSegs - 1) / kSegs;
   const int k0 = seg * len, k1 = min(n, k0 + len);
-  iir_segment(tile + j, n, CW, k0, k1, j < ncol && k0 < k1);
+  iir_segment(tile + j, n, L, k0, k1, j < ncol && k0 < k1);
   __syncthreads();
   for (int k = seg; k < n; k += kSegs)
-    if (j < ncol) out[base + (int64_t)k * line_stride + j] = tile[k * CW + j];
+    if (j < ncol) out[base + (int64_t)k * line_stride + j] = tile[k * L + j];
 }
 
-// lines along the contiguous axis.  grid = ceil(n_rows / 32), block = 256, tile [32][n | 1]
+// lines along the contiguous axis.  grid = ceil(n_rows / L), block = 256, tile [L][n | 1]
+template <int L>
 __global__ void __launch_bounds__(256)
 prefilter_rows_seg(double* __restrict__ data, int n, int64_t n_rows) {
   extern __shared__ double tile[];
-  constexpr int R = 32;
+  constexpr int kSegs = 256 / L;
   const int pitch = n | 1;
-  const int64_t row0 = (int64_t)blockIdx.x * R;
-  const int nrow = (int)min((int64_t)R, n_rows - row0);
+  const int64_t row0 = (int64_t)blockIdx.x * L;
+  const int nrow = (int)min((int64_t)L, n_rows - row0);
   double* g = data + row0 * n;
   for (int r = threadIdx.x >> 5; r < nrow; r += 8)
     for (int k = threadIdx.x & 31; k < n; k += 32) tile[r * pitch + k] = g[(int64_t)r * n + k] * kGain;
   __syncthreads();
-  const int r = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  const int r = threadIdx.x & (L - 1), seg = threadIdx.x / L;
   const int len = (n + kSegs - 1) / kSegs;
   const int k0 = seg * len, k1 = min(n, k0 + len);
   iir_segment(tile + r * pitch, n, 1, k0, k1, r < nrow && k0 < k1);
@@ -686,6 +687,15 @@ gather1_kernel(const float* __restrict__ src, int sy, int sx, const Tap* __restr
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int prefilter_lines() {   // lines per shared-memory tile of the segment-parallel prefilter
+  static int v = 0;
+  if (!v) {
+    const char* e = getenv("MICA_PREFILTER_LINES");
+    v = (e && atoi(e) == 32) ? 32 : 16;
+  }
+  return v;
+}
+
 static int g_force_generic = 0;   // tests: run the general kernels on shapes the fast ones would take
 
 constexpr size_t kMaxTileBytes = 200 * 1024;
@@ -696,9 +706,15 @@ static int launch_cols(const TIn* in, double* out, int n, int64_t line_stride, i
   if (n_cols <= 0 || n_outer <= 0 || n <= 0) return MICA_OK;
   size_t per_col = (size_t)n * sizeof(double);
   if (!g_force_generic && n >= kMinSegLine && per_col * 32 <= kMaxTileBytes) {
-    size_t smem = per_col * 32;
-    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prefilter_cols_seg<TIn><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    if (prefilter_lines() == 16) {
+      size_t smem = per_col * 16;
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_cols_seg<TIn, 16><<<dim3((n_cols + 15) / 16, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    } else {
+      size_t smem = per_col * 32;
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_cols_seg<TIn, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    }
   } else if (per_col * 32 <= kMaxTileBytes) {
     size_t smem = per_col * 32;
     MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -718,9 +734,15 @@ static int launch_rows(double* data, int n, int64_t n_rows, cudaStream_t st) {
   if (n <= 0 || n_rows <= 0) return MICA_OK;
   size_t per_row = (size_t)(n | 1) * sizeof(double);
   if (!g_force_generic && n >= kMinSegLine && per_row * 32 <= kMaxTileBytes) {
-    size_t smem = per_row * 32;
-    MICA_CUDA(cudaFuncSetAttribute(prefilter_rows_seg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prefilter_rows_seg<<<(unsigned)ceil_div64(n_rows, 32), 256, smem, st>>>(data, n, n_rows);
+    if (prefilter_lines() == 16) {
+      size_t smem = per_row * 16;
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_rows_seg<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_rows_seg<16><<<(unsigned)ceil_div64(n_rows, 16), 256, smem, st>>>(data, n, n_rows);
+    } else {
+      size_t smem = per_row * 32;
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_rows_seg<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_rows_seg<32><<<(unsigned)ceil_div64(n_rows, 32), 256, smem, st>>>(data, n, n_rows);
+    }
   } else if (per_row * 32 <= kMaxTileBytes) {
     size_t smem = per_row * 32;
     MICA_CUDA(cudaFuncSetAttribute(prefilter_rows<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

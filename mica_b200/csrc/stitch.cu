@@ -44,13 +44,15 @@ __device__ __forceinline__ float softmax3_last(float l0, float l1, float l2) {
   return e2 * __frcp_rn((e0 + e1) + e2);
 }
 
-// grid = (S [core plane a] * ceil(S*S / 256), B), block = 256: one core voxel per thread, so a batch
-// is thousands of small CTAs and the last wave over the 148 SMs is short
+// grid = (B, S [core plane a] * ceil(S*S / 256)), block = 256: one core voxel per thread, so a batch
+// is thousands of small CTAs and the last wave over the 148 SMs is short.  The cube is the FASTEST
+// grid index: cubes that follow each other in the batch are neighbours along the volume's fastest
+// axis (k), so CTAs resident together write adjacent 128-byte runs of the same output rows
 __global__ void __launch_bounds__(256)
 postproc_stitch_kernel(StitchParams P) {
   const int S = P.S, W = P.W;
   const int chunks = (S * S + 255) >> 8;
-  const int a = blockIdx.x / chunks, b = blockIdx.y;
+  const int a = blockIdx.y / chunks, b = blockIdx.x;
   const int i = P.ijk[3 * b + 0], j = P.ijk[3 * b + 1], k = P.ijk[3 * b + 2];
   const int gx = i + a;
   if (gx >= P.X || gx < P.org[0] || gx >= P.org[0] + P.ext[0]) return;
@@ -60,7 +62,7 @@ postproc_stitch_kernel(StitchParams P) {
   const float* aa = P.aa + (int64_t)b * 21 * W3;
   const int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
   {
-    const int e = (blockIdx.x - a * chunks) * 256 + threadIdx.x;
+    const int e = (blockIdx.y - a * chunks) * 256 + threadIdx.x;
     if (e >= S * S) return;
     const int bj = e / S, c = e - bj * S;
     const int gy = j + bj, gz = k + c;
@@ -174,7 +176,7 @@ extern "C" int mica_postproc_stitch(const float* bb, const float* ca, const floa
     P.aa = aa + (int64_t)b0 * 21 * W3;
     P.ijk = ijk + 3 * (int64_t)b0;
     const int chunks = (grid_size * grid_size + 255) / 256;
-    postproc_stitch_kernel<<<dim3(grid_size * chunks, nb), 256, 0, (cudaStream_t)stream>>>(P);
+    postproc_stitch_kernel<<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P);
     MICA_LAUNCH_CHECK("postproc_stitch_kernel");
   }
   return MICA_OK;

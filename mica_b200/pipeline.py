@@ -248,11 +248,13 @@ class MapPipeline:
         return ops.StitchedVolumes(self.cube_shape, self.device)
 
     # ---------------------------------------------------------------- stage 5 (+model)
-    def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None):
+    def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None, on_batch=None):
         """run_inference + reconstruct_volume (utils/predict.py:307-587) without the
         per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits, enqueued
         on the current stream.  With ``prefetch`` the cubes of batch n+1 are cut on a side
-        stream while the model and the softmax/argmax + stitch of batch n run."""
+        stream while the model and the softmax/argmax + stitch of batch n run.
+        ``on_batch(vols, n_done)`` is called after the stitch of each batch has been enqueued
+        (``n_done`` cubes of ``ijk_host`` are then final in ``vols``, in stream order)."""
         if self.normalized is None:
             raise MicaError('no normalised map')
         self.cube_index()
@@ -268,6 +270,8 @@ class MapPipeline:
                 bb, ca, aa = model_fn(x, af)
                 with self.timer('postproc_stitch'):
                     ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+                if on_batch is not None:
+                    on_batch(vols, b1)
             return vols
 
         t_enqueue = time.perf_counter()
@@ -297,12 +301,14 @@ class MapPipeline:
             consumed[i & 1].record(main)
             with self.timer('postproc_stitch'):
                 ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+            if on_batch is not None:
+                on_batch(vols, b1)
             cur = nxt
         self.last_loop_enqueue_ms = (time.perf_counter() - t_enqueue) * 1e3     # host side of the batch loop
         return vols
 
     # ------------------------------------------------------------------ whole path
-    def run(self, src, header, atoms, model_fn, vols=None):
+    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None):
         """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
         device tensors or None.  Raises on the reference's normalisation failures."""
         self.resample_and_normalize(src, header, defer_status=True)
@@ -310,7 +316,7 @@ class MapPipeline:
             self.encode_af3(*atoms, defer_status=True)
         else:
             self.af3, self._atoms_binned = None, False
-        vols = self.predict_and_stitch(model_fn, vols)
+        vols = self.predict_and_stitch(model_fn, vols, on_batch)
         # one host read-back for the whole path (the reference reports these per stage)
         if not self.check_status():
             raise MicaError(f'normalisation failed (status {self.norm_status})')
@@ -319,11 +325,56 @@ class MapPipeline:
         return vols
 
 
+class _SlabDrain:
+    """Streams finished parts of the stitched volumes to pinned host memory while later cube
+    batches are still being processed.  Cubes are visited i-major (utils/create_grids.py:143-145),
+    so once every cube of an i-layer is stitched the planes [i, i + grid_size) of the [x,y,z]
+    volumes are final and contiguous: they go out on side streams behind an event."""
+
+    def __init__(self, pipe, out_host, n_streams=2):
+        self.pipe, self.out = pipe, out_host
+        self.streams = [torch.cuda.Stream(pipe.device) for _ in range(n_streams)]
+        self.sent_layers = 0
+        self.bytes = 0
+        self.turn = 0
+
+    def __call__(self, vols, n_done):
+        ijk = self.pipe.ijk_host
+        n = len(ijk)
+        # i-layers whose last cube has been stitched
+        if n_done >= n:
+            layer_end = vols.ext[0]
+        else:
+            layer_end = int(ijk[n_done][0]) - vols.org[0]      # cubes [0, n_done) cover x < i of the next cube
+        x0 = self.sent_layers
+        if layer_end <= x0:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.pipe.device))
+        for k, v in vols.as_dict().items():
+            dst = self.out[k]
+            parts = [(dst[x0:layer_end], v[x0:layer_end])] if v.dim() == 3 else \
+                    [(dst[c, x0:layer_end], v[c, x0:layer_end]) for c in range(v.shape[0])]
+            for d, s_ in parts:
+                st = self.streams[self.turn % len(self.streams)]
+                self.turn += 1
+                st.wait_event(ev)
+                with torch.cuda.stream(st):
+                    d.copy_(s_, non_blocking=True)
+                self.bytes += s_.numel() * s_.element_size()
+        self.sent_layers = layer_end
+
+    def finish(self):
+        for st in self.streams:
+            st.synchronize()
+
+
 def run_map_pipeline_host(src_host: torch.Tensor, header: MapHeader, atoms_host, model_fn, pipe: MapPipeline,
-                          out_host: dict | None = None):
+                          out_host: dict | None = None, vols=None, overlap_d2h: bool = True):
     """The call a user of the reference makes, with HOST buffers on both sides: pinned
     source map (+ atom arrays) in, the four stitched volumes out in pinned host memory.
-    Returns (volumes dict of host tensors, h2d_bytes, d2h_bytes)."""
+    With ``overlap_d2h`` finished x-layers of the volumes are copied out while the remaining
+    cube batches run.  Returns (volumes dict of host tensors, h2d_bytes, d2h_bytes)."""
     dev = pipe.device
     src = src_host.to(dev, non_blocking=True)
     h2d = src_host.numel() * src_host.element_size()
@@ -331,7 +382,13 @@ def run_map_pipeline_host(src_host: torch.Tensor, header: MapHeader, atoms_host,
     if atoms_host is not None:
         atoms = tuple(t.to(dev, non_blocking=True) for t in atoms_host)
         h2d += sum(t.numel() * t.element_size() for t in atoms_host)
-    vols = pipe.run(src, header, atoms, model_fn)
+    if out_host is not None and overlap_d2h:
+        drain = _SlabDrain(pipe, out_host)
+        vols = pipe.run(src, header, atoms, model_fn, vols, on_batch=drain)
+        drain.finish()
+        torch.cuda.current_stream().synchronize()
+        return dict(out_host), h2d, drain.bytes
+    vols = pipe.run(src, header, atoms, model_fn, vols)
     d2h = 0
     out = {}
     for k, v in vols.as_dict().items():

@@ -465,3 +465,34 @@ def test_stitch_cubes_plain_paste_and_roundtrip(cuda):
     cubes = ops.extract_cubes(dev(vol, cuda), ijk, 48, 8)
     back = ops.stitch_cubes(cubes, ijk, cube_shape, 48, 8).cpu().numpy()
     assert np.array_equal(back, vol.transpose(0, 3, 2, 1))
+
+
+# ------------------------------------------------------------ host-buffer API (the e2e path of bench.py)
+@pytest.mark.parametrize('batch', [3, 7, 64])
+def test_host_api_overlapped_drain_equals_plain_copy(cuda, batch):
+    """run_map_pipeline_host streams finished x-layers of the volumes to pinned memory while later
+    batches run; the result must equal copying the finished volumes afterwards."""
+    from mica_b200.pdb import channel_codes
+    from mica_b200.pipeline import MapHeader, MapPipeline, run_map_pipeline_host
+    src = synthetic.synthetic_map((40, 36, 52), voxel=1.2, seed=3)
+    hdr = MapHeader(voxel_size=(np.float32(1.2),) * 3)
+    n_out = ops.zoom_output_shape(src.shape, [np.float32(1.2)] * 3)
+    st = synthetic.synthetic_structure(80, n_out[::-1], seed=3)
+    bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
+    src_h = torch.from_numpy(src).pin_memory()
+    atoms_h = tuple(torch.from_numpy(a).pin_memory() for a in (st['coords'], bb_ch, aa_ch))
+    pipe = MapPipeline(cuda, 16, 8, batch_cubes=batch)
+    W = 32
+    gen = torch.Generator(device=cuda).manual_seed(1)
+    ring = tuple(torch.randn((batch, c, W, W, W), generator=gen, device=cuda) for c in (4, 4, 21))
+
+    def model_fn(x, af):
+        return tuple(t[:x.shape[0]] for t in ring)
+
+    plain, h2d, d2h = run_map_pipeline_host(src_h, hdr, atoms_h, model_fn, pipe, None)
+    shape = tuple(plain['backbone_probability'].shape)
+    out_h = {k: torch.full(v.shape, -1.0).pin_memory() for k, v in plain.items()}
+    got, h2d2, d2h2 = run_map_pipeline_host(src_h, hdr, atoms_h, model_fn, pipe, out_h)
+    assert h2d == h2d2 and d2h == d2h2 == 23 * 4 * int(np.prod(shape))
+    for k in plain:
+        assert torch.equal(got[k], plain[k]), k
