@@ -60,11 +60,15 @@ class StageTimer:
     recorded around every stage call; ``summary()`` (after a synchronize) returns
     {stage: (calls, total_ms)}."""
 
-    def __init__(self):
+    def __init__(self, only=None):
         self.spans = []
+        self.only = set(only) if only is not None else None     # time just these stages (events are not free)
 
     @contextmanager
     def __call__(self, name):
+        if self.only is not None and name not in self.only:
+            yield
+            return
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         try:

@@ -341,15 +341,17 @@ def postprocess(bb_logits, ca_logits, aa_logits):
 # ----------------------------------------------------------------------------
 # R8  stitching  (utils/predict.py:439-512)
 # ----------------------------------------------------------------------------
-def stitch(cube_preds, meta, orig_shape, map_type, padding=8):
+def stitch(cube_preds, meta, orig_shape, map_type, padding=8, volume=None):
     """utils/predict.py:458-501: centre-crop paste of the disjoint cores.
     ``cube_preds`` [n,W,W,W] (or [n,20,W,W,W] for 'amino_acid_probability');
     ``meta`` rows (i,j,k,di,dj,dk).  The volume is float32 for every map type
-    (int64 predictions are cast on assignment, :462)."""
-    if map_type == 'amino_acid_probability':
-        volume = np.zeros((20, *orig_shape), dtype=np.float32)
-    else:
-        volume = np.zeros(tuple(orig_shape), dtype=np.float32)
+    (int64 predictions are cast on assignment, :462).  ``volume``: paste into this
+    array (a chunk of the cubes at a time) instead of a fresh zero volume."""
+    if volume is None:
+        if map_type == 'amino_acid_probability':
+            volume = np.zeros((20, *orig_shape), dtype=np.float32)
+        else:
+            volume = np.zeros(tuple(orig_shape), dtype=np.float32)
     p = padding
     for grid, (i, j, k, di, dj, dk) in zip(cube_preds, meta):
         if map_type == 'amino_acid_probability':
@@ -388,3 +390,47 @@ def pipeline_front(src, voxel_size_xyz, coords, bb_ch, aa_ch, origin_xyz,
     af3_cubes = np.stack([extract_cubes(af3[c], grid_size=grid_size, padding=padding)[0]
                           for c in range(24)], axis=1)
     return norm, af3, cubes[:, None], af3_cubes, meta, orig_shape, offset
+
+
+def pipeline_whole_streamed(src, voxel_size_xyz, coords, bb_ch, aa_ch, origin_xyz, logits_ring,
+                            grid_size=48, padding=8, order=3):
+    """The whole path map -> four stitched volumes with the cubes handled a chunk at a time, so a
+    large sample fits in host memory (bench.py's CPU arm).  Same arithmetic as pipeline_front +
+    postprocess_and_stitch; ``logits_ring`` = (bb [c,4,W^3], ca [c,4,W^3], aa [c,21,W^3]) stands
+    where the model stands and is reused for every chunk of c cubes, as the GPU arm's ring is.
+    Returns (volumes dict, number of working-grid voxels, number of cubes)."""
+    res = resample(src, voxel_size_xyz, order=order)
+    norm, med, p = normalize(res)
+    if norm is None:
+        raise RuntimeError('normalisation failed')
+    af3, ok = af3_encode(coords, bb_ch, aa_ch, origin_xyz, norm.shape)
+    if not ok:
+        af3 = np.zeros_like(af3)
+    order_, _ = transpose_order(1, 2, 3, (0, 0, 0))
+    vol_t = np.transpose(norm, order_)                      # utils/create_grids.py:119-122
+    af3_t = np.transpose(af3, (0,) + tuple(1 + o for o in order_))
+    orig_shape = vol_t.shape
+    W = grid_size + 2 * padding
+    pads = [(padding, W - (orig_shape[a] % grid_size)) for a in range(3)]
+    padded = np.pad(vol_t, pads, 'constant')               # :135-139, once per channel in the reference
+    padded_af3 = np.pad(af3_t, [(0, 0)] + pads, 'constant')
+    origins = cube_origins(orig_shape, grid_size)
+    chunk = logits_ring[0].shape[0]
+    vols = {'backbone_probability': np.zeros(orig_shape, np.float32),
+            'carbon_alpha_probability': np.zeros(orig_shape, np.float32),
+            'amino_acid_prediction': np.zeros(orig_shape, np.float32),
+            'amino_acid_probability': np.zeros((20,) + tuple(orig_shape), np.float32)}
+    for c0 in range(0, len(origins), chunk):
+        sel = origins[c0:c0 + chunk]
+        # the model's two inputs (dataset/dataset.py:194-224); materialised as the reference does
+        x = np.stack([padded[i:i + W, j:j + W, k:k + W] for i, j, k in sel])[:, None]
+        af = np.stack([padded_af3[:, i:i + W, j:j + W, k:k + W] for i, j, k in sel])
+        assert x.shape[1:] == (1, W, W, W) and af.shape[1:] == (24, W, W, W)
+        n = len(sel)
+        bb, ca, aa_prob, aa_pred = postprocess(logits_ring[0][:n], logits_ring[1][:n], logits_ring[2][:n])
+        meta = [(i, j, k, min(grid_size, orig_shape[0] - i), min(grid_size, orig_shape[1] - j),
+                 min(grid_size, orig_shape[2] - k)) for i, j, k in sel]
+        for name, pred in (('backbone_probability', bb), ('carbon_alpha_probability', ca),
+                           ('amino_acid_prediction', aa_pred), ('amino_acid_probability', aa_prob)):
+            stitch(pred, meta, orig_shape, name, padding, volume=vols[name])
+    return vols, int(norm.size), len(origins)

@@ -125,3 +125,24 @@ def test_training_twins_match_reference_golden(golden_dir, tmp_path):
     coords, bb, aa, _ = read_pdb_atoms(str(pdb_path))
     vol, ok = orc.af3_encode(coords, bb, aa, g['origin'], g['enc_map'].shape)
     assert ok and np.array_equal(np.argwhere(vol > 0).astype(np.int32), g['enc_nonzero'])
+
+
+def test_streamed_whole_path_equals_front_plus_stitch():
+    """bench.py's CPU arm (chunked, bounded memory) is the same arithmetic as the one-shot functions."""
+    src = synthetic.synthetic_map((20, 24, 18), voxel=1.2, seed=3)
+    voxel = (np.float32(1.2),) * 3
+    n_out = orc.zoom_output_shape(src.shape, orc.zoom_factors(voxel))
+    st = synthetic.synthetic_structure(30, n_out[::-1], seed=3)
+    bb_ch, aa_ch = orc.channel_codes(st['atom_names'], st['res_names'])
+    norm, af3, x, af, meta, shp, _ = orc.pipeline_front(src, voxel, st['coords'], bb_ch, aa_ch, (0, 0, 0), 16, 8)
+    ring = synthetic.synthetic_logits(len(meta), 32, seed=1)
+    want = orc.postprocess_and_stitch(*ring, meta, shp, 8)
+    for chunk in (len(meta), 3):
+        r = tuple(t[:chunk] for t in ring)
+        if chunk < len(meta):       # the ring is reused per chunk: build the matching one-shot logits
+            idx = np.arange(len(meta)) % chunk
+            want = orc.postprocess_and_stitch(*(t[idx] for t in r), meta, shp, 8)
+        vols, nvox, ncubes = orc.pipeline_whole_streamed(src, voxel, st['coords'], bb_ch, aa_ch, (0, 0, 0), r, 16, 8)
+        assert nvox == norm.size and ncubes == len(meta)
+        for k in want:
+            assert np.array_equal(vols[k], want[k]), k
