@@ -177,7 +177,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(['nvidia-smi', f'--id={index}', f'--query-gpu={self.FIELDS}',
-                                       '--format=csv,noheader,nounits', '-lms', '100'],
+                                       '--format=csv,noheader,nounits', '-lms', '20'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass

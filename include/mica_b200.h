@@ -41,6 +41,7 @@ typedef void* mica_stream_t; /* cudaStream_t */
 #define MICA_NORM_NO_POSITIVE 1 /* utils/preprocessing.py:155-157 */
 #define MICA_NORM_ZERO_PCTL 2   /* utils/preprocessing.py:152-154 */
 #define MICA_NORM_PENDING 3     /* selection not finished */
+#define MICA_NORM_PEER_TIMEOUT 4 /* multi-GPU: a peer rank never published its histogram */
 
 #define MICA_SELECT_HIST_WORDS 4096 /* int64 words the histogram all-reduce covers */
 #define MICA_SELECT_PASSES 5        /* hist/pick rounds for median + percentile */
@@ -106,6 +107,25 @@ int mica_select_result(const void* workspace, float* median, float* p999, int64_
  * Reads median / percentile from the workspace on the device; leaves y untouched
  * when the status is not MICA_NORM_OK. */
 int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* workspace, mica_stream_t stream);
+
+/* ------------------------------------------- multi-GPU: histogram exchange over peer memory
+ * No reference counterpart (the reference is single-process); replaces the NCCL all-reduce
+ * between mica_select_hist and mica_select_pick.  Every rank allocates one peer buffer
+ * (mica_peer_alloc; cudaMalloc + a 64-byte CUDA IPC handle), the ranks exchange the handles
+ * (any channel), open each other's (mica_peer_open) and upload the table of `world` device
+ * pointers (own buffer at [rank]).  mica_select_peer_reduce then does, in ONE single-CTA
+ * kernel on the caller's stream: publish the local histogram, signal every peer, wait for
+ * every peer's signal (bounded spin: on timeout the normalisation status becomes
+ * MICA_NORM_PEER_TIMEOUT), sum the peers' histograms over NVLink into the local state.
+ * `parity` = round & 1, `epoch` = a counter every rank increments once per call (>= 1).
+ */
+size_t mica_peer_buffer_bytes(void);
+int mica_peer_alloc(void** dev_ptr, void* ipc_handle_out /* 64 bytes, nullable */);
+int mica_peer_open(const void* ipc_handle, void** dev_ptr);
+int mica_peer_close(void* dev_ptr);
+int mica_peer_free(void* dev_ptr);
+int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, int rank, int world, int parity, int epoch,
+                            mica_stream_t stream);
 
 /* test hooks for the normaliser: (1) evaluate the NumPy expression operation by operation for
  * every voxel instead of the short equivalent path (returns the previous setting); (2) put

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libmica_b200.so')
 
 MICA_OK = 0
 ERR_NAMES = {-1: 'MICA_ERR_INVALID', -2: 'MICA_ERR_CUDA', -3: 'MICA_ERR_WORKSPACE', -4: 'MICA_ERR_NO_DEVICE'}
-NORM_OK, NORM_NO_POSITIVE, NORM_ZERO_PCTL, NORM_PENDING = 0, 1, 2, 3
+NORM_OK, NORM_NO_POSITIVE, NORM_ZERO_PCTL, NORM_PENDING, NORM_PEER_TIMEOUT = 0, 1, 2, 3, 4
 SELECT_HIST_WORDS = 4096
 SELECT_PASSES = 5
 
@@ -53,6 +53,12 @@ SIGNATURES = {
     'mica_normalize_apply_f32': (_i, [_p, _p, _i64, _p, _p]),
     'mica_normalize_force_reference_arith': (_i, [_i]),
     'mica_select_set_thresholds': (_i, [_p, _f, _f, _p]),
+    'mica_peer_buffer_bytes': (_sz, []),
+    'mica_peer_alloc': (_i, [C.POINTER(_p), _p]),
+    'mica_peer_open': (_i, [_p, C.POINTER(_p)]),
+    'mica_peer_close': (_i, [_p]),
+    'mica_peer_free': (_i, [_p]),
+    'mica_select_peer_reduce': (_i, [_p, _p, _i, _i, _i, _i, _p]),
     'mica_af3_encode': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     'mica_af3_bins_workspace_bytes': (_sz, [_i64, _i, _i, _i, C.POINTER(_i), _i, _i]),
     'mica_af3_bin_atoms': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i,

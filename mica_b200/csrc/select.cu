@@ -13,6 +13,8 @@
 //
 // All state lives in a device workspace; the host only sequences launches, so a
 // multi-GPU run can all-reduce hist[] between `hist` and `pick` on the stream.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace mica {
@@ -354,6 +356,67 @@ select_pick_kernel(SelectState* s) {
   }
 }
 
+
+// ---------------------------------------------------- histogram all-reduce over peer memory
+// Multi-GPU order statistics need the SUM of every rank's histogram between `hist` and `pick`
+// (5 times per map).  Through NCCL that is 5 small collectives with a stream hand-over each
+// (measured: +1.7 ms per step on 8 GPUs).  Here the exchange is one single-CTA kernel over
+// NVLink peer memory: every rank owns a small buffer that all peers have mapped (CUDA IPC);
+// the kernel publishes the local histogram in the round's slot, raises a flag in every peer's
+// buffer, waits for the peers' flags and sums their slots (P2P loads) into the local state.
+// Slots alternate with the round parity: a slot is rewritten two rounds later, and a rank can
+// only get there after every peer has signalled the round in between, i.e. finished reading.
+constexpr int kPeerSlotWords = MICA_SELECT_HIST_WORDS;          // int64 words per slot
+constexpr int kPeerMaxWorld = 64;
+constexpr size_t kPeerBufferBytes = 2 * kPeerSlotWords * sizeof(long long) + kPeerMaxWorld * sizeof(int) * 2;
+
+struct PeerBuffer {
+  long long slot[2][kPeerSlotWords];
+  int flag[kPeerMaxWorld];     // flag[p] = last epoch rank p has published
+  int pad[kPeerMaxWorld];
+};
+
+__global__ void __launch_bounds__(1024)
+select_peer_reduce_kernel(SelectState* __restrict__ s, PeerBuffer* const* __restrict__ peers, int rank, int world,
+                          int parity, int epoch, long long timeout_cycles) {
+  __shared__ int ok;
+  PeerBuffer* mine = peers[rank];
+  long long* local = &s->hist[0][0];
+  for (int i = threadIdx.x; i < kPeerSlotWords; i += blockDim.x) mine->slot[parity][i] = local[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < world) {   // raise my flag in every peer's buffer (and my own)
+    volatile int* f = &peers[threadIdx.x]->flag[rank];
+    *f = epoch;
+  }
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < world) {   // wait for peer threadIdx.x
+    volatile int* f = &mine->flag[threadIdx.x];
+    const long long t0 = clock64();
+    while (*f - epoch < 0) {
+      if (clock64() - t0 > timeout_cycles) {
+        ok = 0;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (!ok) {                   // a peer never arrived: fail the normalisation instead of hanging the GPU
+    if (threadIdx.x == 0) {
+      s->status = MICA_NORM_PEER_TIMEOUT;
+      s->round = MICA_SELECT_PASSES;
+    }
+    return;
+  }
+  for (int i = threadIdx.x; i < kPeerSlotWords; i += blockDim.x) {
+    long long sum = 0;
+    for (int p = 0; p < world; ++p) sum += *((volatile long long*)&peers[p]->slot[parity][i]);
+    local[i] = sum;
+  }
+}
+
 __global__ void select_init_kernel(SelectState* s, long long n_total) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < kBins) {
@@ -485,6 +548,54 @@ extern "C" int mica_select_pick(void* workspace, mica_stream_t stream) {
   MICA_REQUIRE(workspace, "null workspace");
   select_pick_kernel<<<1, kPickThreads, 0, (cudaStream_t)stream>>>(state_of(workspace));
   MICA_LAUNCH_CHECK("select_pick_kernel");
+  return MICA_OK;
+}
+
+
+// ---- peer buffers (CUDA IPC) and the fused exchange
+extern "C" size_t mica_peer_buffer_bytes(void) { return kPeerBufferBytes; }
+
+extern "C" int mica_peer_alloc(void** dev_ptr, void* ipc_handle_out) {
+  MICA_REQUIRE(dev_ptr, "null pointer");
+  void* p = nullptr;
+  MICA_CUDA(cudaMalloc(&p, kPeerBufferBytes));
+  MICA_CUDA(cudaMemset(p, 0, kPeerBufferBytes));
+  if (ipc_handle_out) {
+    cudaIpcMemHandle_t h;
+    MICA_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  *dev_ptr = p;
+  return MICA_OK;
+}
+
+extern "C" int mica_peer_open(const void* ipc_handle, void** dev_ptr) {
+  MICA_REQUIRE(ipc_handle && dev_ptr, "null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, ipc_handle, sizeof(h));
+  MICA_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return MICA_OK;
+}
+
+extern "C" int mica_peer_close(void* dev_ptr) {
+  if (dev_ptr) MICA_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+  return MICA_OK;
+}
+
+extern "C" int mica_peer_free(void* dev_ptr) {
+  if (dev_ptr) MICA_CUDA(cudaFree(dev_ptr));
+  return MICA_OK;
+}
+
+extern "C" int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, int rank, int world, int parity,
+                                       int epoch, mica_stream_t stream) {
+  MICA_REQUIRE(workspace && peer_bufs, "null pointer");
+  MICA_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world");
+  MICA_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
+  const long long timeout_cycles = 4000000000LL;   // ~2 s at 1.9 GHz
+  select_peer_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      state_of(workspace), reinterpret_cast<PeerBuffer* const*>(peer_bufs), rank, world, parity, epoch, timeout_cycles);
+  MICA_LAUNCH_CHECK("select_peer_reduce_kernel");
   return MICA_OK;
 }
 

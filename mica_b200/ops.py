@@ -85,21 +85,26 @@ class OrderStats:
         off = lib.mica_select_hist_ptr(self._p) - self.ws.data_ptr()
         return self.ws[off:off + 8 * _lib.SELECT_HIST_WORDS].view(torch.int64)
 
-    def run(self, x: torch.Tensor, n_total: int | None = None, all_reduce=None):
-        """``all_reduce(hist_int64_tensor)`` is called between hist and pick when given
-        (multi-GPU: torch.distributed.all_reduce over NCCL on the current stream)."""
+    def run(self, x: torch.Tensor, n_total: int | None = None, all_reduce=None, peer=None):
+        """Multi-GPU: the histograms of all ranks are summed between hist and pick, either by
+        ``peer`` (a peer.PeerHistogram: one fused kernel over NVLink peer memory) or by
+        ``all_reduce(hist_int64_tensor)`` (torch.distributed.all_reduce over NCCL), both on the
+        current stream."""
         p_x = _dev(x, torch.float32, 'x')
         n_local = x.numel()
         n_total = n_local if n_total is None else int(n_total)
         st = _stream()
-        if all_reduce is None:
+        if all_reduce is None and peer is None:
             check(lib.mica_order_stats_f32(p_x, n_local, self._p, st), 'order_stats')
             return self
         check(lib.mica_select_init(self._p, n_total, st), 'select_init')
-        hist = self.hist_view()
-        for _ in range(_lib.SELECT_PASSES):
+        hist = self.hist_view() if peer is None else None
+        for r in range(_lib.SELECT_PASSES):
             check(lib.mica_select_hist(p_x, n_local, self._p, st), 'select_hist')
-            all_reduce(hist)
+            if peer is not None:
+                peer.reduce(self, r)
+            else:
+                all_reduce(hist)
             check(lib.mica_select_pick(self._p, st), 'select_pick')
         return self
 

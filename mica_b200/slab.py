@@ -127,11 +127,24 @@ class SlabPipeline(MapPipeline):
     of source planes (global planes [own_lo, own_hi) of ``global_src_shape``)."""
 
     def __init__(self, device, rank, world, grid_size=48, padding=8, order=3, batch_cubes=16,
-                 target_voxel_size=1.0, halo_k=16, global_src_shape=None, group=None, af3_mode='sparse'):
+                 target_voxel_size=1.0, halo_k=16, global_src_shape=None, group=None, af3_mode='sparse',
+                 hist_exchange='peer'):
         super().__init__(device, grid_size, padding, order, batch_cubes, target_voxel_size, af3_mode)
         self.rank, self.world, self.halo_k, self.group = int(rank), int(world), halo_k, group
         self.global_src_shape = global_src_shape
         self.plan = None
+        #: 'peer' = one fused publish/signal/wait/sum kernel over NVLink peer memory per radix round
+        #: (peer.PeerHistogram, built on first use); 'nccl' = torch.distributed.all_reduce
+        if hist_exchange not in ('peer', 'nccl'):
+            raise MicaError(f'hist_exchange must be peer or nccl, got {hist_exchange!r}')
+        self.hist_exchange = hist_exchange
+        self.peer = None
+
+    def _peer_group(self):
+        if self.peer is None:
+            from .peer import PeerHistogram
+            self.peer = PeerHistogram(self.device, self.rank, self.world, self.group)
+        return self.peer
 
     # -- collectives (torch.distributed over NCCL; injectable for single-process emulation)
     def _all_reduce_hist(self, hist):
@@ -179,7 +192,11 @@ class SlabPipeline(MapPipeline):
         res, owned = self.slab_resample(own_src, header)
         nz, ny, nx = self.plan.out_shape
         with self.timer('order_stats'):
-            self.stats = ops.OrderStats(self.device).run(owned, n_total=nz * ny * nx, all_reduce=self._all_reduce_hist)
+            if self.hist_exchange == 'peer' and self.world > 1:
+                self.stats = ops.OrderStats(self.device).run(owned, n_total=nz * ny * nx, peer=self._peer_group())
+            else:
+                self.stats = ops.OrderStats(self.device).run(owned, n_total=nz * ny * nx,
+                                                             all_reduce=self._all_reduce_hist)
         self.slab_normalize(res)
         return True if defer_status else self.check_status()
 

@@ -96,3 +96,40 @@ def test_emulated_slab_ranks_match_single_gpu(cuda, world, src_shape, voxel, gs,
             assert torch.equal(vols[k], t), k          # same logits, same cores -> identical volumes
     o_norm, _, _ = orc.normalize(orc.resample(src, hdr.voxel_size))
     assert np.abs(got_norm.cpu().numpy() - o_norm).max() <= 1e-5
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_peer_memory_histogram_exchange_equals_single_gpu(cuda, world):
+    """mica_select_peer_reduce (publish / signal / wait / sum in one kernel over peer-mapped buffers)
+    with `world` emulated ranks on their own streams: thresholds must equal the whole-array run."""
+    import ctypes as C
+    from mica_b200.peer import PeerHistogram
+    lib = _lib.lib
+    g = torch.Generator(device=cuda).manual_seed(world)
+    x = torch.randn(3_000_001, generator=g, device=cuda) * 0.05
+    x[::50] += torch.rand(x[::50].shape, generator=g, device=cuda)
+    want = ops.OrderStats(cuda).run(x).result()
+    bounds = [0] + sorted(int(v) // 4 * 4 for v in torch.randint(1, x.numel() - 1, (world - 1,)).tolist()) + [x.numel()]
+    parts = [x[bounds[r]:bounds[r + 1]] for r in range(world)]
+    groups = PeerHistogram.emulate(cuda, world)
+    streams = [torch.cuda.Stream(cuda) for _ in range(world)]
+    stats = [ops.OrderStats(cuda) for _ in range(world)]
+    torch.cuda.synchronize()
+    for repeat in range(2):                              # epochs keep counting across maps
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                st = C.c_void_p(streams[r].cuda_stream)
+                _lib.check(lib.mica_select_init(stats[r]._p, x.numel(), st))
+        for rnd in range(_lib.SELECT_PASSES):
+            for r in range(world):
+                with torch.cuda.stream(streams[r]):
+                    st = C.c_void_p(streams[r].cuda_stream)
+                    _lib.check(lib.mica_select_hist(C.c_void_p(parts[r].data_ptr()), parts[r].numel(), stats[r]._p, st))
+                    groups[r].reduce(stats[r], rnd, streams[r].cuda_stream)
+                    _lib.check(lib.mica_select_pick(stats[r]._p, st))
+        torch.cuda.synchronize()
+        for r in range(world):
+            got = stats[r].result()
+            assert got[3] == 0, f'rank {r}: status {got[3]}'
+            assert got[:3] == want[:3], (r, got, want)
+    groups[0].close()
