@@ -229,8 +229,13 @@ def run_ours(args):
     src_np = synthetic.synthetic_map((e, e, e), voxel=args.voxel, seed=2022 + rank)
     header = MapHeader(voxel_size=(np.float32(args.voxel),) * 3)
     n_out = ops.zoom_output_shape(src_np.shape, [np.float32(args.voxel)] * 3)
-    # atoms are replicated on every rank (a few MB) and span the whole (stacked) working grid
-    st = synthetic.synthetic_structure(20000 * world, (n_out[2], n_out[1], n_out[0] * world), seed=2022)
+    # atoms are replicated on every rank (a few MB) and span the whole (stacked) working grid: one
+    # 20 k-residue chain per slab, so that every rank has the same AF3 work (weak scaling)
+    parts = [synthetic.synthetic_structure(20000, (n_out[2], n_out[1], n_out[0]), seed=2022 + r) for r in range(world)]
+    for r, part in enumerate(parts):
+        part['coords'][:, 2] += np.float32(r * n_out[0])
+    st = {k: (np.concatenate([p_[k] for p_ in parts]) if isinstance(parts[0][k], np.ndarray)
+              else sum((list(p_[k]) for p_ in parts), [])) for k in parts[0]}
     bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
     src_host = torch.from_numpy(src_np).pin_memory()
     atoms_host = (torch.from_numpy(st['coords']).pin_memory(), torch.from_numpy(bb_ch).pin_memory(),

@@ -223,50 +223,40 @@ af3_scan_kernel(BinWorkspace ws, int n) {
   if (threadIdx.x == 0) ws.offsets[n] = carry;
 }
 
-constexpr int kFillParts = 8;
+constexpr int kFillBlocks = 16;
 
 __device__ __forceinline__ int cube_id_of(const BinParams& P, const int32_t* __restrict__ ijk, int slot) {
   return ((ijk[3 * slot] / P.S) * P.ncube[1] + ijk[3 * slot + 1] / P.S) * P.ncube[2] + ijk[3 * slot + 2] / P.S;
 }
 
-// grid = (kFillParts, slots).  Slot b currently shows cube ijk_prev[b] (b < n_prev, else it is clean) and
-// is switched to cube ijk_next[b] (b < n_next, else it is left clean).  The CTAs of a slot share its entry
-// lists; each owns the voxels with (offset / 4) % kFillParts == blockIdx.x, so "clear the old cube, then
-// set the new one" stays ordered per voxel inside one CTA while the scattered 4-byte stores of a slot
-// spread over kFillParts CTAs.  Stateless: the caller says what the slots hold.
-__global__ void __launch_bounds__(128)
+// grid = (kFillBlocks, slots), launched twice on the stream: SET == false clears the voxels of the cube
+// slot b currently shows (ijk_prev[b], b < n_prev; clean otherwise), SET == true then sets those of
+// ijk_next[b] (b < n_next; left clean otherwise).  A voxel can be in both lists, so "clear, then set"
+// must stay ordered -- the kernel boundary does that, and inside a launch every entry is independent:
+// the entries of a slot spread over kFillBlocks CTAs, which keeps densely populated cubes cheap.
+// Stateless: the caller says what the slots hold.
+template <bool SET>
+__global__ void __launch_bounds__(256)
 af3_fill_cubes_kernel(BinWorkspace ws, BinParams P, const int32_t* __restrict__ ijk_prev, int n_prev,
                       const int32_t* __restrict__ ijk_next, int n_next, float* __restrict__ out,
                       int64_t out_cube_stride, int32_t* __restrict__ nonzero) {
   const int slot = blockIdx.y;
-  const unsigned part = blockIdx.x;
-  float* cube = out + (int64_t)slot * out_cube_stride;
-  const int64_t W3 = (int64_t)P.W * P.W * P.W;
   const int prev = slot < n_prev ? cube_id_of(P, ijk_prev, slot) : -1;
   const int next = slot < n_next ? cube_id_of(P, ijk_next, slot) : -1;
-  if (prev >= 0 && prev != next) {
-    const int e0 = ws.offsets[prev], e1 = ws.offsets[prev + 1];
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const unsigned v = ws.entries[e];
-      const unsigned off = v >> 8, b = v & 7u, r = (v >> 3) & 31u;
-      if (((off >> 2) & (kFillParts - 1)) != part) continue;
-      if (b) cube[(int64_t)(b - 1) * W3 + off] = 0.0f;
-      if (r) cube[(int64_t)(r + 3) * W3 + off] = 0.0f;
-    }
-  }
-  __syncthreads();   // a voxel cleared for the old cube may be set again for the new one
-  if (next >= 0 && prev != next) {
-    const int e0 = ws.offsets[next], e1 = ws.offsets[next + 1];
-    for (int e = e0 + threadIdx.x; e < e1; e += blockDim.x) {
-      const unsigned v = ws.entries[e];
-      const unsigned off = v >> 8, b = v & 7u, r = (v >> 3) & 31u;
-      if (((off >> 2) & (kFillParts - 1)) != part) continue;
-      if (b) cube[(int64_t)(b - 1) * W3 + off] = 1.0f;
-      if (r) cube[(int64_t)(r + 3) * W3 + off] = 1.0f;
-    }
-  }
-  if (threadIdx.x == 0 && part == 0 && nonzero && slot < n_next)
+  if (SET && blockIdx.x == 0 && threadIdx.x == 0 && nonzero && next >= 0)
     nonzero[slot] = (ws.offsets[next + 1] > ws.offsets[next]) ? 1 : 0;
+  const int id = SET ? next : prev;
+  if (id < 0 || prev == next) return;
+  float* cube = out + (int64_t)slot * out_cube_stride;
+  const int64_t W3 = (int64_t)P.W * P.W * P.W;
+  const float val = SET ? 1.0f : 0.0f;
+  const int e0 = ws.offsets[id], e1 = ws.offsets[id + 1];
+  for (int e = e0 + blockIdx.x * 256 + threadIdx.x; e < e1; e += kFillBlocks * 256) {
+    const unsigned v = ws.entries[e];
+    const unsigned off = v >> 8, b = v & 7u, r = (v >> 3) & 31u;
+    if (b) cube[(int64_t)(b - 1) * W3 + off] = val;
+    if (r) cube[(int64_t)(r + 3) * W3 + off] = val;
+  }
 }
 
 static size_t a256(size_t v) { return (v + 255) / 256 * 256; }
@@ -369,8 +359,15 @@ extern "C" int mica_af3_fill_cubes(const void* workspace, int64_t n_atoms, int n
   MICA_REQUIRE(n_slots <= 65535, "too many slots");
   const int n_cubes = P.ncube[0] * P.ncube[1] * P.ncube[2];
   BinWorkspace ws = carve(const_cast<void*>(workspace), n_cubes, bin_capacity(n_atoms, grid_size, padding));
-  af3_fill_cubes_kernel<<<dim3(kFillParts, n_slots), 128, 0, (cudaStream_t)stream>>>(
-      ws, P, ijk_prev, n_prev, ijk_next, n_next, out, out_cube_stride, nonzero);
-  MICA_LAUNCH_CHECK("af3_fill_cubes_kernel");
+  if (n_prev > 0) {
+    af3_fill_cubes_kernel<false><<<dim3(kFillBlocks, n_prev), 256, 0, (cudaStream_t)stream>>>(
+        ws, P, ijk_prev, n_prev, ijk_next, n_next, out, out_cube_stride, nonzero);
+    MICA_LAUNCH_CHECK("af3_fill_cubes_kernel<clear>");
+  }
+  if (n_next > 0) {
+    af3_fill_cubes_kernel<true><<<dim3(kFillBlocks, n_next), 256, 0, (cudaStream_t)stream>>>(
+        ws, P, ijk_prev, n_prev, ijk_next, n_next, out, out_cube_stride, nonzero);
+    MICA_LAUNCH_CHECK("af3_fill_cubes_kernel<set>");
+  }
   return MICA_OK;
 }
