@@ -44,7 +44,7 @@ typedef void* mica_stream_t; /* cudaStream_t */
 #define MICA_NORM_PEER_TIMEOUT 4 /* multi-GPU: a peer rank never published its histogram */
 
 #define MICA_SELECT_HIST_WORDS 4096 /* int64 words the histogram all-reduce covers */
-#define MICA_SELECT_PASSES 5        /* hist/pick rounds for median + percentile */
+#define MICA_SELECT_PASSES 7        /* hist/pick steps: sample, guided digit 0, fallback digit 0, 4 digit rounds */
 
 int mica_version(void);
 const char* mica_last_error(void);
@@ -90,14 +90,19 @@ int mica_bspline_resample_f32(const float* src, int sz, int sy, int sx, int src_
  * State lives in a device workspace so that multi-GPU runs can all-reduce the
  * histogram (MICA_SELECT_HIST_WORDS int64 at mica_select_hist_ptr) between
  * mica_select_hist and mica_select_pick without a host round trip.
- * Protocol: init; repeat MICA_SELECT_PASSES times { hist; [all-reduce]; pick }.
+ * Protocol: init; for step = 0 .. MICA_SELECT_PASSES-1 { hist(step); [all-reduce]; pick(step) }.
+ * Steps: 0 = 1/64 sample histogram -> candidate bins; 1 = guided digit-0 pass (only voxels in
+ * the candidate bins are histogrammed, the others counted) + verification on the exact counts;
+ * 2 = full digit-0 histogram, a no-op unless the verification failed; 3..6 = median digits 1,2
+ * and percentile digits 1,2.  Every kernel checks the device-side state, so the host never
+ * branches on results.
  */
 size_t mica_select_workspace_bytes(void);
 int mica_select_init(void* workspace, int64_t n_total, mica_stream_t stream);
-int mica_select_hist(const float* x, int64_t n_local, void* workspace, mica_stream_t stream);
+int mica_select_hist(const float* x, int64_t n_local, void* workspace, int step, mica_stream_t stream);
 int64_t* mica_select_hist_ptr(void* workspace);
-int mica_select_pick(void* workspace, mica_stream_t stream);
-/* all five rounds on one GPU */
+int mica_select_pick(void* workspace, int step, mica_stream_t stream);
+/* every step on one GPU */
 int mica_order_stats_f32(const float* x, int64_t n, void* workspace, mica_stream_t stream);
 /* synchronises the stream; any out pointer may be NULL */
 int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
@@ -131,6 +136,8 @@ int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, int rank, i
  * every voxel instead of the short equivalent path (returns the previous setting); (2) put
  * given thresholds into a select workspace as if mica_order_stats_f32 had found them. */
 int mica_normalize_force_reference_arith(int on);
+/* test hook: on != 0 makes the guided digit-0 pass fail its verification (exercises the fallback step) */
+int mica_select_force_fallback(int on);
 int mica_select_set_thresholds(void* workspace, float median, float p, mica_stream_t stream);
 
 /* ------------------------------------------------------------ R4 AF3 encoder

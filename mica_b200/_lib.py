@@ -15,7 +15,7 @@ MICA_OK = 0
 ERR_NAMES = {-1: 'MICA_ERR_INVALID', -2: 'MICA_ERR_CUDA', -3: 'MICA_ERR_WORKSPACE', -4: 'MICA_ERR_NO_DEVICE'}
 NORM_OK, NORM_NO_POSITIVE, NORM_ZERO_PCTL, NORM_PENDING, NORM_PEER_TIMEOUT = 0, 1, 2, 3, 4
 SELECT_HIST_WORDS = 4096
-SELECT_PASSES = 5
+SELECT_PASSES = 7
 
 
 class MicaError(RuntimeError):
@@ -45,9 +45,10 @@ SIGNATURES = {
     'mica_bspline_resample_f32': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     'mica_select_workspace_bytes': (_sz, []),
     'mica_select_init': (_i, [_p, _i64, _p]),
-    'mica_select_hist': (_i, [_p, _i64, _p, _p]),
+    'mica_select_hist': (_i, [_p, _i64, _p, _i, _p]),
     'mica_select_hist_ptr': (_p, [_p]),
-    'mica_select_pick': (_i, [_p, _p]),
+    'mica_select_pick': (_i, [_p, _i, _p]),
+    'mica_select_force_fallback': (_i, [_i]),
     'mica_order_stats_f32': (_i, [_p, _i64, _p, _p]),
     'mica_select_result': (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(_i), _p]),
     'mica_normalize_apply_f32': (_i, [_p, _p, _i64, _p, _p]),

@@ -20,6 +20,7 @@
 namespace mica {
 
 constexpr int kBins = 2048;
+constexpr int kDigitRounds = 5;   // digit passes: median 0,1,2 + percentile 1,2 (digit 0 of the percentile reuses hist0)
 
 struct SelectState {
   // histograms first: this is the region the multi-GPU all-reduce covers
@@ -37,7 +38,9 @@ struct SelectState {
   float median;
   float p;
   float g;                    // percentile interpolation weight
-  int pad;
+  int phase0;                 // digit 0: 0 = sample pending, 1 = guided pass pending, 2 = full pass pending, 3 = done
+  int cand[3];                // candidate digit-0 bins from the sample: median in [cand0, cand1], percentile >= cand2
+  int pad2;
 };
 
 static_assert(sizeof(long long) * 2 * kBins == MICA_SELECT_HIST_WORDS * 8, "hist words");
@@ -102,7 +105,7 @@ __global__ void __launch_bounds__(512)
 select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
   __shared__ unsigned h[2 * kBins];
   const int round = s->round;
-  if (round == 0 || round >= MICA_SELECT_PASSES || s->status != MICA_NORM_PENDING) return;   // round 0: select_hist0_kernel
+  if (round == 0 || round >= kDigitRounds || s->phase0 != 3 || s->status != MICA_NORM_PENDING) return;   // digit 0 has its own kernels
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) h[i] = 0;
   __syncthreads();
   const int digit = round_digit(round);
@@ -185,7 +188,7 @@ constexpr long long kHist0MaxPerWarp = 60000;
 __global__ void __launch_bounds__(512)
 select_hist0_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
   extern __shared__ unsigned short hw_all[];   // [kHist0Warps][kBins]
-  if (s->round != 0 || s->status != MICA_NORM_PENDING) return;
+  if (s->phase0 != 2 || s->status != MICA_NORM_PENDING) return;   // the fallback of the guided pass
   for (int i = threadIdx.x; i < kHist0Warps * kBins / 2; i += blockDim.x) reinterpret_cast<unsigned*>(hw_all)[i] = 0u;
   __syncthreads();
   unsigned short* hw = hw_all + (threadIdx.x >> 5) * kBins;
@@ -225,6 +228,108 @@ select_hist0_kernel(const float* __restrict__ x, long long n, SelectState* __res
   }
 }
 
+// ---- digit 0 from a sampled pivot.  A 1/64 sample (select_sample_kernel, same histogram) tells where
+// the median and the 99.9 % tail will fall: a few candidate bins [A_lo, A_hi] around the sample
+// median and everything from P_lo (sample quantile 0.997) upwards.  The guided pass then histograms
+// only the voxels inside the candidate bins exactly; every other voxel just bumps one of two
+// register counters ("below A_lo", "between A_hi and P_lo"), whose totals are lumped into bins
+// A_lo-1 and P_lo-1.  The pick verifies on these EXACT counts that both median ranks fall inside
+// [A_lo, A_hi] and that the tail from P_lo holds more voxels than any percentile rank can skip;
+// otherwise select_hist0_kernel (the full histogram) runs as the fallback round.  ~96 % of the
+// voxels of a density map take the two-instruction path.
+constexpr int kSampleStride = 64;   // float4 stride of the sample
+
+__global__ void __launch_bounds__(512)
+select_sample_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
+  __shared__ unsigned h[kBins];
+  if (s->phase0 != 0 || s->status != MICA_NORM_PENDING) return;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  long long head = (4 - (long long)(((uintptr_t)x >> 2) & 3)) & 3;
+  if (head > n) head = n;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const long long n4 = (n - head) >> 2, ns4 = (n4 + kSampleStride - 1) / kSampleStride;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < ns4; i += stride) {
+    const float4 v = x4[i * kSampleStride];
+    atomicAdd(&h[f32_key(nan_to_num_f32(v.x)) >> 21], 1u);
+    atomicAdd(&h[f32_key(nan_to_num_f32(v.y)) >> 21], 1u);
+    atomicAdd(&h[f32_key(nan_to_num_f32(v.z)) >> 21], 1u);
+    atomicAdd(&h[f32_key(nan_to_num_f32(v.w)) >> 21], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    unsigned c = h[i];
+    if (c) atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[0][0]) + i, (unsigned long long)c);
+  }
+}
+
+__global__ void __launch_bounds__(512)
+select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
+  __shared__ unsigned h[kBins];
+  __shared__ unsigned long long lump[2];
+  if (s->phase0 != 1 || s->status != MICA_NORM_PENDING) return;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
+  if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
+  __syncthreads();
+  const unsigned a_lo = (unsigned)s->cand[0], a_w = (unsigned)(s->cand[1] - s->cand[0]), p_lo = (unsigned)s->cand[2];
+  unsigned c0 = 0, c1 = 0;   // voxels below A_lo / between A_hi and P_lo seen by this thread
+  auto classify = [&](float v, unsigned& bin) -> bool {
+    bin = f32_key(nan_to_num_f32(v)) >> 21;
+    const bool below = bin < a_lo, exact = (bin - a_lo <= a_w) | (bin >= p_lo);
+    c0 += below ? 1u : 0u;
+    c1 += (below | exact) ? 0u : 1u;
+    return exact;
+  };
+  long long head = (4 - (long long)(((uintptr_t)x >> 2) & 3)) & 3;
+  if (head > n) head = n;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const long long n4 = (n - head) >> 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  unsigned bin;
+  if (tid < head && classify(x[tid], bin)) atomicAdd(&h[bin], 1u);
+  for (long long i = head + n4 * 4 + tid; i < n; i += stride)
+    if (classify(x[i], bin)) atomicAdd(&h[bin], 1u);
+  const long long n4_pad = (n4 + 31) & ~31LL;
+  for (long long i = tid; i < n4_pad; i += stride) {
+    const bool ok = i < n4;
+    const float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const bool exact = ok && classify(vv[c], bin);
+      const unsigned m = __ballot_sync(0xffffffffu, exact);
+      if (m == 0u) continue;
+      if (__popc(m) <= 8) {            // a few candidates: plain shared atomics
+        if (exact) atomicAdd(&h[bin], 1u);
+      } else if (exact) {              // many (ties, masked maps): one atomic per distinct bin
+        const unsigned peers = __match_any_sync(m, bin);
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
+      }
+    }
+  }
+  // block totals of the two counters
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (c0) atomicAdd(&lump[0], (unsigned long long)c0);
+    if (c1) atomicAdd(&lump[1], (unsigned long long)c1);
+  }
+  __syncthreads();
+  unsigned long long* gh = reinterpret_cast<unsigned long long*>(&s->hist[0][0]);
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    unsigned c = h[i];
+    if (c) atomicAdd(gh + i, (unsigned long long)c);
+  }
+  if (threadIdx.x == 0) {
+    if (lump[0]) atomicAdd(gh + (a_lo > 0 ? a_lo - 1 : 0), lump[0]);
+    if (lump[1]) atomicAdd(gh + (p_lo > 0 ? p_lo - 1 : 0), lump[1]);
+  }
+}
+
 // 1 block x kPickThreads threads, two bins per thread.  Finds the bucket holding `rank`.
 constexpr int kPickThreads = kBins / 2;
 
@@ -254,37 +359,126 @@ __device__ void pick_bucket(const long long* hist, long long rank, int* bucket, 
   __syncthreads();
 }
 
+// Host step t (0 .. MICA_SELECT_PASSES-1) -> what the pick does, gated on the device-side state so that
+// a step whose pass did not run (e.g. the fallback round after a successful guided pass) is a no-op:
+//   t = 0  sample histogram     -> candidate bins (phase0 0 -> 1)
+//   t = 1  guided digit-0 pass  -> verify; commit digit 0 (phase0 1 -> 3, round 0 -> 1) or ask for the fallback (1 -> 2)
+//   t = 2  full digit-0 pass    -> commit digit 0 (phase0 2 -> 3); no-op unless phase0 == 2
+//   t = 3..6                    -> digit rounds 1..4 (median digits 1, 2; percentile digits 1, 2)
 __global__ void __launch_bounds__(kPickThreads)
-select_pick_kernel(SelectState* s) {
+select_pick_kernel(SelectState* s, int t) {
   __shared__ long long scratch[kPickThreads];
-  __shared__ int bucket[2];
-  __shared__ long long below[2], count[2];
-  const int round = s->round;
-  if (round >= MICA_SELECT_PASSES || s->status != MICA_NORM_PENDING) return;
-  const int digit = round_digit(round);
-  const bool same = (s->prefix[0] == s->prefix[1]);
-  if (threadIdx.x < 2) {
+  __shared__ int bucket[3];
+  __shared__ long long below[3], count[3];
+  __shared__ long long tail_count;
+  __shared__ int verdict;
+  if (s->status != MICA_NORM_PENDING) return;
+  const int phase0 = s->phase0;
+  int round;   // digit round to commit, or -1
+  if (t == 0) {
+    if (phase0 != 0) return;
+    round = -1;
+  } else if (t == 1) {
+    if (phase0 != 1) return;
+    round = 0;
+  } else if (t == 2) {
+    if (phase0 != 2) return;
+    round = 0;
+  } else {
+    round = t - 2;
+    if (phase0 != 3 || s->round != round || round >= kDigitRounds) return;
+  }
+  if (threadIdx.x < 3) {
     bucket[threadIdx.x] = -1;
     below[threadIdx.x] = 0;
     count[threadIdx.x] = 0;
   }
+  if (threadIdx.x == 0) {
+    tail_count = 0;
+    verdict = 1;
+  }
   __syncthreads();
+
+  if (t == 0) {
+    // ---- candidate bins from the sample: sample quantiles 0.48 / 0.52 bracket the median, 0.997 the tail
+    long long part = s->hist[0][2 * threadIdx.x] + s->hist[0][2 * threadIdx.x + 1];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long*>(&tail_count), (unsigned long long)part);
+    __syncthreads();
+    const long long ns = tail_count;
+    const long long ranks[3] = {(long long)(0.48 * (double)ns), (long long)(0.52 * (double)ns), (long long)(0.997 * (double)ns)};
+    if (ns >= 4096)
+      for (int q = 0; q < 3; ++q) pick_bucket(s->hist[0], ranks[q] < ns ? ranks[q] : ns - 1, &bucket[q], &below[q], &count[q], scratch);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int a_lo = 0, a_hi = kBins - 1, p_lo = 0;   // tiny inputs: everything is histogrammed exactly
+      if (ns >= 4096 && bucket[0] >= 0 && bucket[1] >= bucket[0] && bucket[2] >= 0) {
+        a_lo = bucket[0];
+        a_hi = bucket[1];
+        p_lo = bucket[2] > a_hi ? bucket[2] : a_hi + 1;
+      }
+      s->cand[0] = a_lo;
+      s->cand[1] = a_hi;
+      s->cand[2] = p_lo;
+      s->phase0 = 1;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kBins; i += kPickThreads) {
+      s->hist[0][i] = 0;
+      s->hist[1][i] = 0;
+    }
+    return;
+  }
+
+  const int digit = round_digit(round);
+  const bool same = (s->prefix[0] == s->prefix[1]);
+  for (int q = 0; q < 2; ++q) {
+    const long long* h = (digit == 0 || same) ? s->hist[0] : s->hist[q];
+    pick_bucket(h, s->rank[q], &bucket[q], &below[q], &count[q], scratch);
+  }
+  __syncthreads();
+  if (t == 1) {
+    // ---- verify the guided pass on its exact counts
+    const int a_lo = s->cand[0], a_hi = s->cand[1], p_lo = s->cand[2];
+    long long part = 0;
+    for (int i = threadIdx.x; i < kBins; i += kPickThreads)
+      if (i >= p_lo) part += s->hist[0][i];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long*>(&tail_count), (unsigned long long)part);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      // every percentile rank is >= 0.9995 N - 1 (at least half of the voxels are <= the median);
+      // the margin covers the float32 virtual index of NumPy 2
+      const long long need = (long long)(0.00052 * (double)s->n_total) + 64;
+      const bool med_ok = bucket[0] >= a_lo && bucket[0] <= a_hi && bucket[1] >= a_lo && bucket[1] <= a_hi;
+      const bool tail_ok = (p_lo == 0) || tail_count >= need;
+      if (!(med_ok && tail_ok)) {
+        verdict = 0;
+        s->phase0 = 2;      // run the full histogram (host step 2)
+      }
+    }
+    __syncthreads();
+    if (!verdict) {
+      for (int i = threadIdx.x; i < kBins; i += kPickThreads) {
+        s->hist[0][i] = 0;
+        s->hist[1][i] = 0;
+      }
+      return;
+    }
+  }
   if (round == 0) {  // keep the digit-0 histogram for the percentile phase
     s->hist0[threadIdx.x] = s->hist[0][threadIdx.x];
     s->hist0[threadIdx.x + kPickThreads] = s->hist[0][threadIdx.x + kPickThreads];
   }
-  for (int t = 0; t < 2; ++t) {
-    const long long* h = (digit == 0 || same) ? s->hist[0] : s->hist[t];
-    pick_bucket(h, s->rank[t], &bucket[t], &below[t], &count[t], scratch);
-  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int t = 0; t < 2; ++t) {
-      int b = bucket[t] < 0 ? 0 : bucket[t];  // unreachable for consistent counts
-      s->prefix[t] = digit == 0 ? (unsigned)b : ((s->prefix[t] << (digit == 1 ? 11 : 10)) | (unsigned)b);
-      s->rank[t] -= below[t];
-      s->below[t] += below[t];
-      s->count_eq[t] = count[t];
+    if (round == 0) s->phase0 = 3;
+    for (int q = 0; q < 2; ++q) {
+      int b = bucket[q] < 0 ? 0 : bucket[q];  // unreachable for consistent counts
+      s->prefix[q] = digit == 0 ? (unsigned)b : ((s->prefix[q] << (digit == 1 ? 11 : 10)) | (unsigned)b);
+      s->rank[q] -= below[q];
+      s->below[q] += below[q];
+      s->count_eq[q] = count[q];
     }
     if (round == 2) {
       // ---- median (np.median on float32): N odd -> s[N/2]; N even -> f32((a + b) / 2)
@@ -298,7 +492,7 @@ select_pick_kernel(SelectState* s) {
       s->n_pos = npos;
       if (npos <= 0) {
         s->status = MICA_NORM_NO_POSITIVE;
-        s->round = MICA_SELECT_PASSES;
+        s->round = kDigitRounds;
       } else {
         // ---- np.percentile(pos, 99.9), float32 virtual index (NumPy >= 2)
         float q = __fdiv_rn(99.9f, 100.0f);
@@ -330,7 +524,7 @@ select_pick_kernel(SelectState* s) {
       s->p = r;
       s->status = (r != 0.0f) ? MICA_NORM_OK : MICA_NORM_ZERO_PCTL;
     }
-    if (s->round < MICA_SELECT_PASSES) s->round = round + 1;
+    if (s->round < kDigitRounds) s->round = round + 1;
   }
   __syncthreads();
   // clear the exchange histograms for the next round
@@ -340,22 +534,22 @@ select_pick_kernel(SelectState* s) {
   }
   __syncthreads();
   if (round == 2 && s->status == MICA_NORM_PENDING) {
-    // percentile digit 0 comes from the saved whole-array histogram (no extra data pass)
+    // percentile digit 0 comes from the saved whole-array histogram (no extra data pass); after a
+    // guided pass its bins below cand[2] are lumped, and the verification guarantees the ranks lie above
     __shared__ int b2[2];
     __shared__ long long bl2[2], c2[2];
-    for (int t = 0; t < 2; ++t) pick_bucket(s->hist0, s->rank[t], &b2[t], &bl2[t], &c2[t], scratch);
+    for (int q = 0; q < 2; ++q) pick_bucket(s->hist0, s->rank[q], &b2[q], &bl2[q], &c2[q], scratch);
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (int t = 0; t < 2; ++t) {
-        s->prefix[t] = (unsigned)b2[t];
-        s->rank[t] -= bl2[t];
-        s->below[t] = bl2[t];
-        s->count_eq[t] = c2[t];
+      for (int q = 0; q < 2; ++q) {
+        s->prefix[q] = (unsigned)b2[q];
+        s->rank[q] -= bl2[q];
+        s->below[q] = bl2[q];
+        s->count_eq[q] = c2[q];
       }
     }
   }
 }
-
 
 // ---------------------------------------------------- histogram all-reduce over peer memory
 // Multi-GPU order statistics need the SUM of every rank's histogram between `hist` and `pick`
@@ -406,7 +600,7 @@ select_peer_reduce_kernel(SelectState* __restrict__ s, PeerBuffer* const* __rest
   if (!ok) {                   // a peer never arrived: fail the normalisation instead of hanging the GPU
     if (threadIdx.x == 0) {
       s->status = MICA_NORM_PEER_TIMEOUT;
-      s->round = MICA_SELECT_PASSES;
+      s->round = kDigitRounds;
     }
     return;
   }
@@ -433,6 +627,10 @@ __global__ void select_init_kernel(SelectState* s, long long n_total) {
     s->count_eq[0] = s->count_eq[1] = 0;
     s->prefix[0] = s->prefix[1] = 0;
     s->round = 0;
+    s->phase0 = 0;
+    s->cand[0] = 0;
+    s->cand[1] = kBins - 1;
+    s->cand[2] = 0;
     s->status = n_total > 0 ? MICA_NORM_PENDING : MICA_NORM_NO_POSITIVE;
     s->n_le_med = 0;
     s->n_pos = 0;
@@ -519,38 +717,72 @@ extern "C" int mica_select_init(void* workspace, int64_t n_total, mica_stream_t 
   return MICA_OK;
 }
 
-// Both kernels are launched every round; each returns at once unless the device-side round counter
-// says the pass is its own (round 0 -> select_hist0_kernel, rounds 1..4 -> select_hist_kernel), so
-// the host never needs to read the state back.
-extern "C" int mica_select_hist(const float* x, int64_t n_local, void* workspace, mica_stream_t stream) {
+// One data pass of host step t (see select_pick_kernel).  Every kernel re-checks the device-side state and
+// returns at once when the step is not due (the fallback step 2 after a successful guided pass), so
+// the host never reads the state back between steps.
+extern "C" int mica_select_hist(const float* x, int64_t n_local, void* workspace, int step, mica_stream_t stream) {
   MICA_REQUIRE(workspace && (x || n_local == 0), "null pointer");
   MICA_REQUIRE(n_local >= 0, "negative n");
+  MICA_REQUIRE(step >= 0 && step < MICA_SELECT_PASSES, "select step %d out of range", step);
   if (n_local == 0) return MICA_OK;
-  int64_t want = ceil_div64(ceil_div64(n_local, 4), 512);
-  int grid = (int)(want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4);
-  select_hist_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(x, n_local, state_of(workspace));
-  MICA_LAUNCH_CHECK("select_hist_kernel");
-  // digit 0: at most kHist0MaxPerWarp elements per warp (16-bit counters), at least two CTAs per SM
-  int64_t grid0 = ceil_div64(n_local, kHist0Warps * kHist0MaxPerWarp);
-  if (grid0 < 2 * kNumSMs) grid0 = want < 2 * kNumSMs ? want : 2 * kNumSMs;
-  const size_t smem0 = (size_t)kHist0Warps * kBins * sizeof(unsigned short);
-  static bool attr_set = false;
-  if (!attr_set) {
-    MICA_CUDA(cudaFuncSetAttribute(select_hist0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-    attr_set = true;
+  cudaStream_t st = (cudaStream_t)stream;
+  SelectState* s = state_of(workspace);
+  const int64_t want = ceil_div64(ceil_div64(n_local, 4), 512);
+  const int grid = (int)(want < (int64_t)kNumSMs * 4 ? want : (int64_t)kNumSMs * 4);
+  if (step == 0) {
+    const int64_t ws = ceil_div64(ceil_div64(n_local, 4 * kSampleStride), 512);
+    select_sample_kernel<<<(unsigned)(ws < kNumSMs ? (ws > 0 ? ws : 1) : kNumSMs), 512, 0, st>>>(x, n_local, s);
+    MICA_LAUNCH_CHECK("select_sample_kernel");
+  } else if (step == 1) {
+    select_hist0_guided_kernel<<<grid, 512, 0, st>>>(x, n_local, s);
+    MICA_LAUNCH_CHECK("select_hist0_guided_kernel");
+  } else if (step == 2) {
+    // full digit-0 histogram: at most kHist0MaxPerWarp elements per warp (16-bit counters), >= two CTAs per SM
+    int64_t grid0 = ceil_div64(n_local, kHist0Warps * kHist0MaxPerWarp);
+    if (grid0 < 2 * kNumSMs) grid0 = want < 2 * kNumSMs ? want : 2 * kNumSMs;
+    const size_t smem0 = (size_t)kHist0Warps * kBins * sizeof(unsigned short);
+    static bool attr_set = false;
+    if (!attr_set) {
+      MICA_CUDA(cudaFuncSetAttribute(select_hist0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+      attr_set = true;
+    }
+    select_hist0_kernel<<<(unsigned)grid0, 512, smem0, st>>>(x, n_local, s);
+    MICA_LAUNCH_CHECK("select_hist0_kernel");
+  } else {
+    select_hist_kernel<<<grid, 512, 0, st>>>(x, n_local, s);
+    MICA_LAUNCH_CHECK("select_hist_kernel");
   }
-  select_hist0_kernel<<<(unsigned)grid0, 512, smem0, (cudaStream_t)stream>>>(x, n_local, state_of(workspace));
-  MICA_LAUNCH_CHECK("select_hist0_kernel");
   return MICA_OK;
 }
 
-extern "C" int mica_select_pick(void* workspace, mica_stream_t stream) {
+static int g_select_force_fallback;
+__global__ void select_spoil_candidates_kernel(SelectState* s);
+
+extern "C" int mica_select_pick(void* workspace, int step, mica_stream_t stream) {
   MICA_REQUIRE(workspace, "null workspace");
-  select_pick_kernel<<<1, kPickThreads, 0, (cudaStream_t)stream>>>(state_of(workspace));
+  MICA_REQUIRE(step >= 0 && step < MICA_SELECT_PASSES, "select step %d out of range", step);
+  select_pick_kernel<<<1, kPickThreads, 0, (cudaStream_t)stream>>>(state_of(workspace), step);
   MICA_LAUNCH_CHECK("select_pick_kernel");
+  if (step == 0 && g_select_force_fallback) {
+    select_spoil_candidates_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state_of(workspace));
+    MICA_LAUNCH_CHECK("select_spoil_candidates_kernel");
+  }
   return MICA_OK;
 }
 
+// test hook: 1 forces the guided pass to be rejected (exercises the full-histogram fallback)
+__global__ void select_spoil_candidates_kernel(SelectState* s) {
+  if (s->phase0 == 1) {   // candidates that cannot contain the median
+    s->cand[0] = kBins - 1;
+    s->cand[1] = kBins - 1;
+    s->cand[2] = kBins - 1;
+  }
+}
+extern "C" int mica_select_force_fallback(int on) {
+  const int was = g_select_force_fallback;
+  g_select_force_fallback = on ? 1 : 0;
+  return was;
+}
 
 // ---- peer buffers (CUDA IPC) and the fused exchange
 extern "C" size_t mica_peer_buffer_bytes(void) { return kPeerBufferBytes; }
@@ -601,9 +833,9 @@ extern "C" int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, 
 
 extern "C" int mica_order_stats_f32(const float* x, int64_t n, void* workspace, mica_stream_t stream) {
   int rc = mica_select_init(workspace, n, stream);
-  for (int r = 0; r < MICA_SELECT_PASSES && rc == MICA_OK; ++r) {
-    rc = mica_select_hist(x, n, workspace, stream);
-    if (rc == MICA_OK) rc = mica_select_pick(workspace, stream);
+  for (int t = 0; t < MICA_SELECT_PASSES && rc == MICA_OK; ++t) {
+    rc = mica_select_hist(x, n, workspace, t, stream);
+    if (rc == MICA_OK) rc = mica_select_pick(workspace, t, stream);
   }
   return rc;
 }
@@ -644,7 +876,8 @@ __global__ void select_set_thresholds_kernel(SelectState* s, float median, float
   s->median = median;
   s->p = p;
   s->status = MICA_NORM_OK;
-  s->round = MICA_SELECT_PASSES;
+  s->round = kDigitRounds;
+  s->phase0 = 3;
 }
 extern "C" int mica_select_set_thresholds(void* workspace, float median, float p, mica_stream_t stream) {
   MICA_REQUIRE(workspace, "null workspace");

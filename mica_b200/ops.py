@@ -100,12 +100,12 @@ class OrderStats:
         check(lib.mica_select_init(self._p, n_total, st), 'select_init')
         hist = self.hist_view() if peer is None else None
         for r in range(_lib.SELECT_PASSES):
-            check(lib.mica_select_hist(p_x, n_local, self._p, st), 'select_hist')
+            check(lib.mica_select_hist(p_x, n_local, self._p, r, st), 'select_hist')
             if peer is not None:
                 peer.reduce(self, r)
             else:
                 all_reduce(hist)
-            check(lib.mica_select_pick(self._p, st), 'select_pick')
+            check(lib.mica_select_pick(self._p, r, st), 'select_pick')
         return self
 
     def result(self):

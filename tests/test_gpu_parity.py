@@ -171,6 +171,39 @@ def test_normalize_short_path_is_bit_identical_to_numpy_arithmetic(cuda):
         assert np.array_equal(ref[:1 << 20].view(np.uint32), want.astype(np.float32).view(np.uint32)), (med, p)
 
 
+def test_order_stats_guided_pass_fallback_and_adversarial_sample(cuda):
+    """The digit-0 pass trusts a 1/64 sample only after verifying it on exact counts: a forced
+    rejection and a map whose sampled voxels are decoys must both give NumPy's thresholds."""
+    rng = np.random.default_rng(21)
+    x = (rng.standard_normal(1 << 22) * 0.05).astype(np.float32)
+    x[::37] += rng.random(x[::37].shape, dtype=np.float32)
+    want = orc.normalize(x)
+    was = _lib.lib.mica_select_force_fallback(1)
+    try:
+        norm, st = ops.normalize(dev(x, cuda))
+    finally:
+        _lib.lib.mica_select_force_fallback(was)
+    med, p, npos, status = st.result()
+    assert status == 0 and np.float32(med) == np.float32(want[1]) and np.float32(p) == np.float32(want[2])
+    assert np.array_equal(norm.cpu().numpy(), want[0])
+    # decoys exactly where the sample looks (every 64th float4 of the 16-byte aligned array)
+    y = x.copy()
+    y.reshape(-1, 256)[:, :4] = 1000.0 + rng.random((y.size // 256, 4), dtype=np.float32)
+    want = orc.normalize(y)
+    norm, st = ops.normalize(dev(y, cuda))
+    med, p, npos, status = st.result()
+    assert status == 0 and np.float32(med) == np.float32(want[1]) and np.float32(p) == np.float32(want[2])
+    assert np.array_equal(norm.cpu().numpy(), want[0])
+    # and the other way round: the sample sees only background, the tail is elsewhere
+    z = x.copy()
+    z.reshape(-1, 256)[:, :4] = 0.0
+    want = orc.normalize(z)
+    norm, st = ops.normalize(dev(z, cuda))
+    med, p, npos, status = st.result()
+    assert status == 0 and np.float32(med) == np.float32(want[1]) and np.float32(p) == np.float32(want[2])
+    assert np.array_equal(norm.cpu().numpy(), want[0])
+
+
 def test_normalize_bit_exact_on_oracle_resampled(cuda, golden_dir):
     """Stage isolation: feed SciPy's own float32 volume to the GPU normaliser."""
     g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))

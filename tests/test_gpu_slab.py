@@ -23,13 +23,13 @@ def _lockstep_stats(ranks, owned, n_total):
     stats = [ops.OrderStats(o.device) for o in owned]
     for s in stats:
         _lib.check(lib.mica_select_init(s._p, n_total, st))
-    for _ in range(_lib.SELECT_PASSES):
+    for step in range(_lib.SELECT_PASSES):
         for s, o in zip(stats, owned):
-            _lib.check(lib.mica_select_hist(C.c_void_p(o.data_ptr()), o.numel(), s._p, st))
+            _lib.check(lib.mica_select_hist(C.c_void_p(o.data_ptr()), o.numel(), s._p, step, st))
         total = sum(s.hist_view().clone() for s in stats)
         for s in stats:
             s.hist_view().copy_(total)
-            _lib.check(lib.mica_select_pick(s._p, st))
+            _lib.check(lib.mica_select_pick(s._p, step, st))
     return stats
 
 
@@ -124,9 +124,9 @@ def test_peer_memory_histogram_exchange_equals_single_gpu(cuda, world):
             for r in range(world):
                 with torch.cuda.stream(streams[r]):
                     st = C.c_void_p(streams[r].cuda_stream)
-                    _lib.check(lib.mica_select_hist(C.c_void_p(parts[r].data_ptr()), parts[r].numel(), stats[r]._p, st))
+                    _lib.check(lib.mica_select_hist(C.c_void_p(parts[r].data_ptr()), parts[r].numel(), stats[r]._p, rnd, st))
                     groups[r].reduce(stats[r], rnd, streams[r].cuda_stream)
-                    _lib.check(lib.mica_select_pick(stats[r]._p, st))
+                    _lib.check(lib.mica_select_pick(stats[r]._p, rnd, st))
         torch.cuda.synchronize()
         for r in range(world):
             got = stats[r].result()
