@@ -69,7 +69,10 @@ __device__ __forceinline__ int round_digit(int r) { return r < 3 ? r : r - 2; }
 
 __device__ __forceinline__ void warp_hist_add(unsigned* h, unsigned bin, bool pred) {
   unsigned act = __ballot_sync(0xffffffffu, pred);
-  if (pred) {
+  if (act == 0u) return;
+  if (__popc(act) <= 8) {          // a few candidates: plain shared atomics
+    if (pred) atomicAdd(&h[bin], 1u);
+  } else if (pred) {               // many (ties): one atomic per distinct bin
     unsigned peers = __match_any_sync(act, bin);
     if ((threadIdx.x & 31) == (unsigned)(__ffs(peers) - 1)) atomicAdd(&h[bin], (unsigned)__popc(peers));
   }
@@ -333,30 +336,48 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
 // 1 block x kPickThreads threads, two bins per thread.  Finds the bucket holding `rank`.
 constexpr int kPickThreads = kBins / 2;
 
-__device__ void pick_bucket(const long long* hist, long long rank, int* bucket, long long* below,
-                            long long* count, long long* scratch /* [kPickThreads] shared */) {
-  const int t = threadIdx.x;
+// Finds, for up to three ranks at once, the bin holding the rank (one scan of the 2048 bins:
+// warp-shuffle scan of the per-thread pair sums + a scan of the 32 warp totals).
+__device__ void pick_buckets(const long long* hist, const long long* ranks, int n_ranks, int* bucket, long long* below,
+                             long long* count, long long* scratch /* [kPickThreads] shared */) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   const long long v0 = hist[2 * t], v1 = hist[2 * t + 1];
-  scratch[t] = v0 + v1;
+  long long incl = v0 + v1;
+  for (int off = 1; off < 32; off <<= 1) {
+    const long long up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += up;
+  }
+  if (lane == 31) scratch[warp] = incl;
   __syncthreads();
-  for (int off = 1; off < kPickThreads; off <<= 1) {  // Hillis-Steele inclusive scan
-    long long add = (t >= off) ? scratch[t - off] : 0;
-    __syncthreads();
-    scratch[t] += add;
-    __syncthreads();
-  }
-  const long long excl0 = scratch[t] - v0 - v1, excl1 = excl0 + v0;
-  if (v0 > 0 && rank >= excl0 && rank < excl0 + v0) {
-    *bucket = 2 * t;
-    *below = excl0;
-    *count = v0;
-  }
-  if (v1 > 0 && rank >= excl1 && rank < excl1 + v1) {
-    *bucket = 2 * t + 1;
-    *below = excl1;
-    *count = v1;
+  if (warp == 0) {
+    long long w = scratch[lane];
+    for (int off = 1; off < 32; off <<= 1) {
+      const long long up = __shfl_up_sync(0xffffffffu, w, off);
+      if (lane >= off) w += up;
+    }
+    scratch[32 + lane] = w;          // inclusive totals of the warps
   }
   __syncthreads();
+  const long long excl0 = incl - v0 - v1 + (warp ? scratch[32 + warp - 1] : 0), excl1 = excl0 + v0;
+  for (int q = 0; q < n_ranks; ++q) {
+    const long long rank = ranks[q];
+    if (v0 > 0 && rank >= excl0 && rank < excl0 + v0) {
+      bucket[q] = 2 * t;
+      below[q] = excl0;
+      count[q] = v0;
+    }
+    if (v1 > 0 && rank >= excl1 && rank < excl1 + v1) {
+      bucket[q] = 2 * t + 1;
+      below[q] = excl1;
+      count[q] = v1;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ void pick_bucket(const long long* hist, long long rank, int* bucket, long long* below,
+                            long long* count, long long* scratch) {
+  pick_buckets(hist, &rank, 1, bucket, below, count, scratch);
 }
 
 // Host step t (0 .. MICA_SELECT_PASSES-1) -> what the pick does, gated on the device-side state so that
@@ -406,9 +427,9 @@ select_pick_kernel(SelectState* s, int t) {
     if ((threadIdx.x & 31) == 0 && part) atomicAdd(reinterpret_cast<unsigned long long*>(&tail_count), (unsigned long long)part);
     __syncthreads();
     const long long ns = tail_count;
-    const long long ranks[3] = {(long long)(0.48 * (double)ns), (long long)(0.52 * (double)ns), (long long)(0.997 * (double)ns)};
-    if (ns >= 4096)
-      for (int q = 0; q < 3; ++q) pick_bucket(s->hist[0], ranks[q] < ns ? ranks[q] : ns - 1, &bucket[q], &below[q], &count[q], scratch);
+    long long ranks[3] = {(long long)(0.48 * (double)ns), (long long)(0.52 * (double)ns), (long long)(0.997 * (double)ns)};
+    for (int q = 0; q < 3; ++q) ranks[q] = ranks[q] < ns ? ranks[q] : ns - 1;
+    if (ns >= 4096) pick_buckets(s->hist[0], ranks, 3, bucket, below, count, scratch);
     __syncthreads();
     if (threadIdx.x == 0) {
       int a_lo = 0, a_hi = kBins - 1, p_lo = 0;   // tiny inputs: everything is histogrammed exactly
@@ -432,9 +453,11 @@ select_pick_kernel(SelectState* s, int t) {
 
   const int digit = round_digit(round);
   const bool same = (s->prefix[0] == s->prefix[1]);
-  for (int q = 0; q < 2; ++q) {
-    const long long* h = (digit == 0 || same) ? s->hist[0] : s->hist[q];
-    pick_bucket(h, s->rank[q], &bucket[q], &below[q], &count[q], scratch);
+  if (digit == 0 || same) {
+    const long long ranks2[2] = {s->rank[0], s->rank[1]};
+    pick_buckets(s->hist[0], ranks2, 2, bucket, below, count, scratch);
+  } else {
+    for (int q = 0; q < 2; ++q) pick_bucket(s->hist[q], s->rank[q], &bucket[q], &below[q], &count[q], scratch);
   }
   __syncthreads();
   if (t == 1) {
@@ -538,7 +561,8 @@ select_pick_kernel(SelectState* s, int t) {
     // guided pass its bins below cand[2] are lumped, and the verification guarantees the ranks lie above
     __shared__ int b2[2];
     __shared__ long long bl2[2], c2[2];
-    for (int q = 0; q < 2; ++q) pick_bucket(s->hist0, s->rank[q], &b2[q], &bl2[q], &c2[q], scratch);
+    const long long ranks2[2] = {s->rank[0], s->rank[1]};
+    pick_buckets(s->hist0, ranks2, 2, b2, bl2, c2, scratch);
     __syncthreads();
     if (threadIdx.x == 0) {
       for (int q = 0; q < 2; ++q) {
