@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument('--voxel', type=float, default=1.2)
     ap.add_argument('--grid-size', type=int, default=32)
     ap.add_argument('--padding', type=int, default=16)
-    ap.add_argument('--batch-cubes', type=int, default=128)
+    ap.add_argument('--batch-cubes', type=int, default=256)
     ap.add_argument('--cpu-edge', type=int, default=0, help='source edge of the CPU sample (0 = auto)')
     ap.add_argument('--e2e-steps', type=int, default=2)
     ap.add_argument('--no-cpu-baseline', action='store_true')

@@ -628,11 +628,33 @@ select_peer_reduce_kernel(SelectState* __restrict__ s, PeerBuffer* const* __rest
     }
     return;
   }
-  for (int i = threadIdx.x; i < kPeerSlotWords; i += blockDim.x) {
-    long long sum = 0;
-    for (int p = 0; p < world; ++p) sum += *((volatile long long*)&peers[p]->slot[parity][i]);
-    local[i] = sum;
+  // sum the peers' slots: all loads of a thread (4 words x up to 4 peers) are issued before the first
+  // is consumed -- one NVLink round trip per group of 4 peers instead of one per load
+  __shared__ const long long* base[kPeerMaxWorld];
+  if (threadIdx.x < world) base[threadIdx.x] = peers[threadIdx.x]->slot[parity];
+  __syncthreads();
+  constexpr int kPer = kPeerSlotWords / 1024;
+  long long sum[kPer];
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) sum[k] = 0;
+  for (int p0 = 0; p0 < world; p0 += 4) {
+    long long v[kPer][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long* b = base[p0 + j < world ? p0 + j : rank];
+#pragma unroll
+      for (int k = 0; k < kPer; ++k)
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v[k][j]) : "l"(b + threadIdx.x + k * 1024));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (p0 + j < world) {
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) sum[k] += v[k][j];
+      }
   }
+#pragma unroll
+  for (int k = 0; k < kPer; ++k) local[threadIdx.x + k * 1024] = sum[k];
 }
 
 __global__ void select_init_kernel(SelectState* s, long long n_total) {
