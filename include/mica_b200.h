@@ -107,6 +107,10 @@ int mica_order_stats_f32(const float* x, int64_t n, void* workspace, mica_stream
 /* synchronises the stream; any out pointer may be NULL */
 int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
                        mica_stream_t stream);
+/* the same without the synchronisation: the 32-byte record {int64 n_le_med, int64 n_pos, float median,
+ * float p999, float g, int32 status} is copied into host_record (pinned memory) in stream order */
+#define MICA_SELECT_RESULT_BYTES 32
+int mica_select_result_async(const void* workspace, void* host_record, mica_stream_t stream);
 /* y = min(m, p)/p with m = (x > med) * (x - med), written exactly as
  * utils/preprocessing.py:124,131-133 evaluates it in float32; x == y allowed.
  * Reads median / percentile from the workspace on the device; leaves y untouched
@@ -122,7 +126,9 @@ int mica_normalize_apply_f32(const float* x, float* y, int64_t n, const void* wo
  * kernel on the caller's stream: publish the local histogram, signal every peer, wait for
  * every peer's signal (bounded spin: on timeout the normalisation status becomes
  * MICA_NORM_PEER_TIMEOUT), sum the peers' histograms over NVLink into the local state.
- * `parity` = round & 1, `epoch` = a counter every rank increments once per call (>= 1).
+ * `epoch` = a counter every rank increments once per call (>= 1), `parity` = epoch & 1: a slot is
+ * rewritten two calls later, which a rank can only reach after every peer has signalled the call in
+ * between, i.e. has finished reading it.
  */
 size_t mica_peer_buffer_bytes(void);
 int mica_peer_alloc(void** dev_ptr, void* ipc_handle_out /* 64 bytes, nullable */);

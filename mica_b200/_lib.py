@@ -51,6 +51,7 @@ SIGNATURES = {
     'mica_select_force_fallback': (_i, [_i]),
     'mica_order_stats_f32': (_i, [_p, _i64, _p, _p]),
     'mica_select_result': (_i, [_p, C.POINTER(_f), C.POINTER(_f), C.POINTER(_i64), C.POINTER(_i), _p]),
+    'mica_select_result_async': (_i, [_p, _p, _p]),
     'mica_normalize_apply_f32': (_i, [_p, _p, _i64, _p, _p]),
     'mica_normalize_force_reference_arith': (_i, [_i]),
     'mica_select_set_thresholds': (_i, [_p, _f, _f, _p]),

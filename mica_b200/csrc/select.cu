@@ -582,8 +582,8 @@ select_pick_kernel(SelectState* s, int t) {
 // NVLink peer memory: every rank owns a small buffer that all peers have mapped (CUDA IPC);
 // the kernel publishes the local histogram in the round's slot, raises a flag in every peer's
 // buffer, waits for the peers' flags and sums their slots (P2P loads) into the local state.
-// Slots alternate with the round parity: a slot is rewritten two rounds later, and a rank can
-// only get there after every peer has signalled the round in between, i.e. finished reading.
+// Slots alternate with the call epoch: a slot is rewritten two calls later, and a rank can only
+// get there after every peer has signalled the call in between, i.e. finished reading.
 constexpr int kPeerSlotWords = MICA_SELECT_HIST_WORDS;          // int64 words per slot
 constexpr int kPeerMaxWorld = 64;
 constexpr size_t kPeerBufferBytes = 2 * kPeerSlotWords * sizeof(long long) + kPeerMaxWorld * sizeof(int) * 2;
@@ -886,24 +886,34 @@ extern "C" int mica_order_stats_f32(const float* x, int64_t n, void* workspace, 
   return rc;
 }
 
-extern "C" int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
-                                  mica_stream_t stream) {
-  MICA_REQUIRE(workspace, "null workspace");
-  struct Tail {
-    long long n_le_med, n_pos;
-    float median, p, g;
-    int pad;
-  } tail;
-  int status = 0;
+// [n_le_med i64][n_pos i64][median f32][p f32][g f32][status i32]
+struct SelectResultRecord {
+  long long n_le_med, n_pos;
+  float median, p, g;
+  int status;
+};
+static_assert(sizeof(SelectResultRecord) == MICA_SELECT_RESULT_BYTES, "result record size");
+
+extern "C" int mica_select_result_async(const void* workspace, void* host_record, mica_stream_t stream) {
+  MICA_REQUIRE(workspace && host_record, "null pointer");
   const SelectState* s = state_of(workspace);
   cudaStream_t st = (cudaStream_t)stream;
-  MICA_CUDA(cudaMemcpyAsync(&tail, &s->n_le_med, sizeof(tail), cudaMemcpyDeviceToHost, st));
-  MICA_CUDA(cudaMemcpyAsync(&status, &s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
-  MICA_CUDA(cudaStreamSynchronize(st));
-  if (median) *median = tail.median;
-  if (p999) *p999 = tail.p;
-  if (n_pos) *n_pos = tail.n_pos;
-  if (norm_status) *norm_status = status;
+  SelectResultRecord* r = (SelectResultRecord*)host_record;
+  MICA_CUDA(cudaMemcpyAsync(r, &s->n_le_med, 28, cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaMemcpyAsync(&r->status, &s->status, sizeof(int), cudaMemcpyDeviceToHost, st));
+  return MICA_OK;
+}
+
+extern "C" int mica_select_result(const void* workspace, float* median, float* p999, int64_t* n_pos, int* norm_status,
+                                  mica_stream_t stream) {
+  SelectResultRecord r;
+  int rc = mica_select_result_async(workspace, &r, stream);
+  if (rc) return rc;
+  MICA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (median) *median = r.median;
+  if (p999) *p999 = r.p;
+  if (n_pos) *n_pos = r.n_pos;
+  if (norm_status) *norm_status = r.status;
   return MICA_OK;
 }
 

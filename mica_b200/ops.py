@@ -115,6 +115,22 @@ class OrderStats:
                                      _stream()), 'select_result')
         return np.float32(med.value), np.float32(p.value), int(npos.value), int(status.value)
 
+    def result_async(self, record: torch.Tensor | None = None) -> torch.Tensor:
+        """Enqueue the copy of the 32-byte result record into pinned host memory (no synchronisation);
+        decode it with ``OrderStats.decode`` once the stream has passed this point."""
+        if record is None:
+            record = torch.zeros(32, dtype=torch.uint8).pin_memory()
+        check(lib.mica_select_result_async(self._p, C.c_void_p(record.data_ptr()), _stream()), 'select_result_async')
+        return record
+
+    @staticmethod
+    def decode(record: torch.Tensor):
+        """(median, p999, n_pos, status) from a result record."""
+        raw = record.numpy()
+        n_pos = int(raw[8:16].view(np.int64)[0])
+        med, p = raw[16:24].view(np.float32)
+        return np.float32(med), np.float32(p), n_pos, int(raw[28:32].view(np.int32)[0])
+
     def apply(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         p_x = _dev(x, torch.float32, 'x')
         if out is None:

@@ -60,10 +60,12 @@ class PeerHistogram:
 
     def reduce(self, stats, round_index: int, stream=None):
         """Sum every rank's histogram of this round into ``stats`` (an ops.OrderStats), in stream order."""
+        # the slot alternates with the EPOCH (not the select step): a map has an odd number of steps, so the
+        # last exchange of one map and the first of the next would otherwise share a slot back to back
         self.epoch += 1
         st = C.c_void_p(stream if stream is not None else torch.cuda.current_stream(self.device).cuda_stream)
         check(lib.mica_select_peer_reduce(stats._p, C.c_void_p(self.table.data_ptr()), self.rank, self.world,
-                                          round_index & 1, self.epoch, st), 'select_peer_reduce')
+                                          self.epoch & 1, self.epoch, st), 'select_peer_reduce')
 
     def close(self):
         torch.cuda.synchronize(self.device)

@@ -124,6 +124,7 @@ class MapPipeline:
         #: cut batch n+1 on a side stream while the model and the stitch of batch n run on the
         #: caller's stream (two input buffers).  False = everything on the caller's stream.
         self.prefetch = True
+        self._deferred = []
         self._pre_stream = None
 
     # ------------------------------------------------------------------ stage 1+2
@@ -311,16 +312,42 @@ class MapPipeline:
         self.last_loop_enqueue_ms = (time.perf_counter() - t_enqueue) * 1e3     # host side of the batch loop
         return vols
 
+    def finish(self):
+        """Wait for every ``run(..., defer_check=True)`` issued so far and raise if one of them failed."""
+        pending, self._deferred = self._deferred, []
+        for rec, af, ev in pending:
+            ev.synchronize()
+            med, p, npos, status = ops.OrderStats.decode(rec)
+            self.norm_status, self.median, self.p999, self.n_pos = status, med, p, npos
+            if status != NORM_OK:
+                raise MicaError(f'normalisation failed (status {status})')
+            if af is not None and int(af[0]) != 0:
+                raise MicaError('AF3 encoding failed: atom index outside the grid (reference IndexError path, D7)')
+
     # ------------------------------------------------------------------ whole path
-    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None):
+    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False):
         """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
-        device tensors or None.  Raises on the reference's normalisation failures."""
+        device tensors or None.  Raises on the reference's normalisation failures -- at once, or,
+        with ``defer_check``, from ``finish()``: the status words are copied to pinned memory in
+        stream order and the host does not wait, so the next map can be enqueued while this one
+        still runs (a stream of maps; per-step host synchronisation also re-aligns the ranks of
+        a multi-GPU run at the cost of their host jitter)."""
         self.resample_and_normalize(src, header, defer_status=True)
         if atoms is not None:
             self.encode_af3(*atoms, defer_status=True)
         else:
             self.af3, self._atoms_binned = None, False
         vols = self.predict_and_stitch(model_fn, vols, on_batch)
+        if defer_check:
+            rec = self.stats.result_async()
+            af = None
+            if atoms is not None:
+                af = torch.zeros(1, dtype=torch.int32).pin_memory()
+                af.copy_(self._af3_status, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._deferred.append((rec, af, ev))
+            return vols
         # one host read-back for the whole path (the reference reports these per stage)
         if not self.check_status():
             raise MicaError(f'normalisation failed (status {self.norm_status})')

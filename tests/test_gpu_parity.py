@@ -529,3 +529,24 @@ def test_host_api_overlapped_drain_equals_plain_copy(cuda, batch):
     assert h2d == h2d2 and d2h == d2h2 == 23 * 4 * int(np.prod(shape))
     for k in plain:
         assert torch.equal(got[k], plain[k]), k
+
+
+def test_deferred_status_check_reports_failures_from_finish(cuda):
+    """run(..., defer_check=True) does not synchronise; finish() raises what run() would have raised."""
+    from mica_b200._lib import MicaError
+    from mica_b200.pipeline import MapHeader, MapPipeline
+    hdr = MapHeader(voxel_size=(np.float32(1.0),) * 3)
+    pipe = MapPipeline(cuda, 16, 8, batch_cubes=8)
+    ring = tuple(torch.zeros((8, c, 32, 32, 32), device=cuda) for c in (4, 4, 21))
+    model_fn = lambda x, af: tuple(t[:x.shape[0]] for t in ring)
+    good = dev(synthetic.synthetic_map((24, 24, 24), voxel=1.0, seed=1), cuda)
+    v1 = pipe.run(good, hdr, None, model_fn)
+    v2 = pipe.run(good, hdr, None, model_fn, defer_check=True)
+    pipe.finish()
+    assert torch.equal(v1.backbone_probability, v2.backbone_probability) and pipe.norm_status == 0
+    flat = torch.full((24, 24, 24), 2.0, device=cuda)           # no voxel above the median
+    pipe.run(flat, hdr, None, model_fn, defer_check=True)        # does not raise here
+    with pytest.raises(MicaError):
+        pipe.finish()
+    with pytest.raises(MicaError):
+        pipe.run(flat, hdr, None, model_fn)
