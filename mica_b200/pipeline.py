@@ -204,9 +204,16 @@ class MapPipeline:
         perm, offset = self.header.transpose_order()
         self.perm, self.offset = perm, offset
         self.cube_shape = ops.cube_space_shape(self.normalized.shape, perm)
-        self.ijk_host = ops.cube_origins(self.cube_shape, self.grid_size)
-        self.ijk = torch.from_numpy(self.ijk_host).to(self.device)
+        self._set_cube_origins(ops.cube_origins(self.cube_shape, self.grid_size), (self.cube_shape, self.grid_size))
         return self.ijk_host
+
+    def _set_cube_origins(self, ijk_host, key):
+        """Upload the cube origins once per geometry: a pageable host->device copy blocks the host until
+        all earlier work of the stream has run, i.e. it would serialise consecutive maps."""
+        if getattr(self, '_ijk_key', None) != key:
+            self.ijk_host = np.ascontiguousarray(ijk_host)
+            self.ijk = torch.from_numpy(self.ijk_host).to(self.device)
+            self._ijk_key = key
 
     def _buffers(self, B, slot=0):
         W = self.window

@@ -226,8 +226,7 @@ class SlabPipeline(MapPipeline):
         self.cube_shape = ops.cube_space_shape(self.plan.out_shape, perm)
         ijk = ops.cube_origins(self.cube_shape, self.grid_size)
         mine = (ijk[:, 2] >= me.out_lo) & (ijk[:, 2] < me.out_hi)
-        self.ijk_host = np.ascontiguousarray(ijk[mine])
-        self.ijk = torch.from_numpy(self.ijk_host).to(self.device)
+        self._set_cube_origins(ijk[mine], (self.cube_shape, self.grid_size, me.out_lo, me.out_hi))
         self.box = ((0, 0, me.out_lo), (self.cube_shape[0], self.cube_shape[1], me.out_hi - me.out_lo))
         return self.ijk_host
 
