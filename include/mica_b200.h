@@ -233,6 +233,84 @@ int mica_stitch_cubes(const float* cubes, int n_ch, const int32_t* ijk, int n_cu
                       int X, int Y, int Z, const int org[3], const int ext[3],
                       int grid_size, int padding, float* vol, mica_stream_t stream);
 
+/* ===================================================================================
+ * SURVEY.md section 8(f) "next" rows, built to the same bar as R1-R8.
+ * =================================================================================== */
+
+/* ------------------------------------------------ N1: C-alpha candidates (Solver.clustering head)
+ * Replaces utils/modeler.py:767-860: threshold -> DBSCAN -> cluster score filter -> greedy NMS ->
+ * 3x3x3 weighted refinement, on the stitched volumes where they lie in HBM (cube space [X,Y,Z],
+ * C order), so that only the picks cross PCIe.  Index work is bit-exact; see candidates.cu for the
+ * two float paths.  "lin" is the C-order linear voxel index x*Y*Z + y*Z + z (int64).
+ */
+/* :767 np.where(vol > thr), two steps because the caller allocates the outputs:
+ * count (device int64 *count_dev; read it after synchronising), then write (ascending lin =
+ * np.where order; xyz_out device int32 [cap,3], nullable).  vol must not change in between. */
+size_t mica_cand_threshold_workspace_bytes(int64_t n_vox);
+int mica_cand_threshold_count(const float* vol, int64_t n_vox, float thr, void* workspace, size_t workspace_bytes,
+                              int64_t* count_dev, mica_stream_t stream);
+int mica_cand_threshold_write(const float* vol, int X, int Y, int Z, float thr, const void* workspace,
+                              int64_t* lin_out, int32_t* xyz_out, int64_t cap, mica_stream_t stream);
+/* out[i] = vol[lin[i]]  (BBProb[pcd[:,0],pcd[:,1],pcd[:,2]], :779) */
+int mica_gather_f32(const float* vol, const int64_t* lin, int64_t n, float* out, mica_stream_t stream);
+/* :768-770 Open3D cluster_dbscan(eps, min_points) on lattice points (closed ball, self included, clusters
+ * numbered by first core point, border point -> first cluster reaching it, noise -1).  eps_sq = floor(eps^2).
+ * lin ascending and distinct.  labels: device int32 [n]; n_clusters_dev: device int64. */
+size_t mica_dbscan_workspace_bytes(int X, int Y, int Z, int64_t n_points);
+int mica_dbscan_lattice(const int64_t* lin, int64_t n, int X, int Y, int Z, int eps_sq, int min_points,
+                        void* workspace, size_t workspace_bytes, int32_t* labels, int64_t* n_clusters_dev,
+                        mica_stream_t stream);
+/* :775-786 per-label sum (float64) and count of vals; labels outside [0,n_labels) are skipped */
+int mica_cand_cluster_scores(const float* vals, const int32_t* labels, int64_t n, int n_labels, double* sums,
+                             int64_t* counts, mica_stream_t stream);
+/* :789-797 valid[i] = label_ok[labels[i]] (0 for noise) */
+int mica_cand_valid_points(const int32_t* labels, const uint8_t* label_ok, int64_t n, int n_labels, uint8_t* valid,
+                           mica_stream_t stream);
+/* :800-802 CAProb_clusted: out = 0 everywhere, ca at the valid points */
+int mica_cand_clustered_volume(const float* ca, int64_t n_vox, const int64_t* lin, const uint8_t* valid, int64_t n,
+                               float* out, mica_stream_t stream);
+/* :805-832 greedy NMS over the valid points (squared distance <= nms_radius_sq suppresses; the reference
+ * compares the squared distance with its `nms_radius` argument).  work: device float32 [X*Y*Z] scratch, holds
+ * -p at the picks afterwards.  flag_dev: device int32.  Synchronises the stream every 8 rounds. */
+int mica_cand_nms(const float* ca, int X, int Y, int Z, const int64_t* lin, const uint8_t* valid, int64_t n,
+                  int nms_radius_sq, float* work, int32_t* flag_dev, int* rounds_out, mica_stream_t stream);
+/* the picks in the reference's order (best probability first, ties by np.where order): sorted_lin device int64
+ * [cap], sorted_xyz device int32 [cap,3]; scratch_* device [cap]; *n_picks_dev device int64 (the call
+ * synchronises to read it and fails with MICA_ERR_WORKSPACE if it exceeds cap). */
+int mica_cand_nms_picks(const float* work, int Y, int Z, const int64_t* lin, const uint8_t* valid, int64_t n,
+                        int64_t cap, int64_t* scratch_lin, float* scratch_p, int64_t* n_picks_dev,
+                        int64_t* sorted_lin, int32_t* sorted_xyz, mica_stream_t stream);
+/* :837-860 per pick: CA_cands (float64 [m,3]), CA_cands_AAProb rows (float32 [m,20]), CA_cands_AA
+ * (float32 [m]) and ok (uint8 [m]; 0 = pick on the volume border, skipped by the reference's try/except). */
+int mica_cand_refine(const float* ca, const float* aa_prob, const float* aa_pred, int X, int Y, int Z,
+                     const int64_t* pick_lin, int64_t m, double* out_xyz, float* out_aaprob, float* out_aa,
+                     uint8_t* out_ok, mica_stream_t stream);
+
+/* ------------------------------------------------ N3: training label masks
+ * scripts_for_training_data/create_backbone_mask.py:136-172, create_carbon_alpha_mask.py:136-173:
+ * xyz device float32 [A,3] of ALL atoms in file order, is_class device uint8 [A]; mask device int32 [nz,ny,nx]
+ * = 3 (class atom) / 2 (other atom; the LAST atom on a voxel wins) / 1 (26-neighbour of an atom voxel) / 0.
+ * clip_* as in mica_af3_encode (the reference clips (x,y,z) with (nz,ny,nx): pass nz-1, ny-1, nx-1);
+ * *status_oob = 1 where numpy would raise IndexError. */
+int mica_label_class_mask(const float* xyz, const uint8_t* is_class, int64_t n_atoms, float ox, float oy, float oz,
+                          int clip_x, int clip_y, int clip_z, int nz, int ny, int nx, int32_t* mask,
+                          int* status_oob, mica_stream_t stream);
+/* scripts_for_training_data/create_amino_acid_mask.py:151-177: xyz device float32 [R,3] C-alpha coordinates in
+ * file order, label device int32 [R] (1..20): lowest label on the 26 neighbours, C-alpha voxels zeroed in order. */
+size_t mica_label_aa_mask_workspace_bytes(int nz, int ny, int nx);
+int mica_label_aa_mask(const float* xyz, const int32_t* label, int64_t n_ca, float ox, float oy, float oz,
+                       int clip_x, int clip_y, int clip_z, int nz, int ny, int nx, void* workspace,
+                       size_t workspace_bytes, int32_t* mask, int* status_oob, mica_stream_t stream);
+
+/* ------------------------------------------------ N4: docking masks
+ * utils/dock_in_map.py:269: out = where(in < level, 0, in) (in == out allowed) */
+int mica_contour_threshold_f32(const float* in, float* out, int64_t n, float level, mica_stream_t stream);
+/* utils/dock_in_map.py:330-352: zero map (device float32 [nz,ny,nx], in place) wherever
+ * distance_transform_edt(~seeds, sampling=voxel_size) <= radius; seeds = int((xyz - origin) / voxel) of the atoms
+ * (device float32 [A,3]) that pass the reference's bounds test.  *status_oob = 1 where numpy would raise. */
+int mica_zero_around_atoms(const float* xyz, int64_t n_atoms, const float origin_xyz[3], const float voxel_xyz[3],
+                           double radius, int nz, int ny, int nx, float* map, int* status_oob, mica_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,25 @@ SIGNATURES = {
     'mica_postproc_stitch': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i,
                                   _p, _p, _p, _p, _p]),
     'mica_stitch_cubes': (_i, [_p, _i, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, _p, _p]),
+    # candidates
+    'mica_cand_threshold_workspace_bytes': (_sz, [_i64]),
+    'mica_cand_threshold_count': (_i, [_p, _i64, _f, _p, _sz, _p, _p]),
+    'mica_cand_threshold_write': (_i, [_p, _i, _i, _i, _f, _p, _p, _p, _i64, _p]),
+    'mica_gather_f32': (_i, [_p, _p, _i64, _p, _p]),
+    'mica_dbscan_workspace_bytes': (_sz, [_i, _i, _i, _i64]),
+    'mica_dbscan_lattice': (_i, [_p, _i64, _i, _i, _i, _i, _i, _p, _sz, _p, _p, _p]),
+    'mica_cand_cluster_scores': (_i, [_p, _p, _i64, _i, _p, _p, _p]),
+    'mica_cand_valid_points': (_i, [_p, _p, _i64, _i, _p, _p]),
+    'mica_cand_clustered_volume': (_i, [_p, _i64, _p, _p, _i64, _p, _p]),
+    'mica_cand_nms': (_i, [_p, _i, _i, _i, _p, _p, _i64, _i, _p, _p, C.POINTER(_i), _p]),
+    'mica_cand_nms_picks': (_i, [_p, _i, _i, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    'mica_cand_refine': (_i, [_p, _p, _p, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p]),
+    # N3: label masks, N4: docking masks
+    'mica_label_class_mask': (_i, [_p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
+    'mica_label_aa_mask_workspace_bytes': (_sz, [_i, _i, _i]),
+    'mica_label_aa_mask': (_i, [_p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _p, _sz, _p, _p, _p]),
+    'mica_contour_threshold_f32': (_i, [_p, _p, _i64, _f, _p]),
+    'mica_zero_around_atoms': (_i, [_p, _i64, C.POINTER(_f), C.POINTER(_f), C.c_double, _i, _i, _i, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

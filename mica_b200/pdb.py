@@ -43,3 +43,32 @@ def read_pdb_atoms(path):
     coords = np.array(xs, dtype=np.float64).astype(np.float32).reshape(-1, 3)
     bb, aa = channel_codes(names, resn)
     return coords, bb, aa, n_res
+
+
+def read_pdb_records(path):
+    """Every ATOM and HETATM record in file order -- what iterating a Bio.PDB structure
+    ``for model / chain / residue / atom`` visits in the label-mask builders
+    (scripts_for_training_data/create_backbone_mask.py:143-147; no hetero filter there).
+    Returns dict(coords float32 [A,3], atom_names [A], res_names [A], res_index int64 [A]);
+    ``res_index`` numbers the residues (a new one starts whenever chain / hetero flag /
+    sequence number / insertion code changes)."""
+    xs, names, resn, ridx = [], [], [], []
+    n_res, last = -1, None
+    with open(path) as f:
+        for line in f:
+            rec = line[:6]
+            if rec.startswith('MODEL'):
+                last = None
+                continue
+            if rec not in ('ATOM  ', 'HETATM'):
+                continue
+            key = (line[21], rec, line[22:27])
+            if key != last:
+                n_res += 1
+                last = key
+            xs.append((line[30:38], line[38:46], line[46:54]))
+            names.append(line[12:16].strip())
+            resn.append(line[17:20].strip())
+            ridx.append(n_res)
+    coords = np.array(xs, dtype=np.float64).astype(np.float32).reshape(-1, 3)
+    return dict(coords=coords, atom_names=names, res_names=resn, res_index=np.asarray(ridx, dtype=np.int64))

@@ -136,3 +136,51 @@ def synthetic_logits(n_cubes, window=64, seed=2022):
         return a
 
     return draw(4), draw(4), draw(21)
+
+
+def synthetic_predictions(shape_xyz, n_residues=(60, 25), seed=2022, spurious=2, wall_margin=3.0):
+    """Stitched-volume look-alikes for the candidate step (utils/modeler.py:762-858): one
+    random-walk C-alpha chain per entry of ``n_residues`` (each confined to its own part of the
+    box so that DBSCAN sees separate clusters) rendered as Gaussian peaks into
+    ``carbon_alpha_probability``, a wider tube for ``backbone_probability``, smooth random
+    ``amino_acid_probability`` [20,X,Y,Z] and its arg-max as float32 (utils/predict.py:462).
+    ``spurious`` adds bright C-alpha blobs with no backbone support (clusters the reference's
+    score filter must drop).  A little noise breaks ties between voxels.  ``wall_margin=0`` lets the
+    chains touch the faces of the box (picks on the border, which the reference skips)."""
+    rng = np.random.default_rng(seed)
+    X, Y, Z = (int(v) for v in shape_xyz)
+    gx, gy, gz = np.meshgrid(np.arange(X), np.arange(Y), np.arange(Z), indexing='ij')
+    ca = np.zeros((X, Y, Z), np.float64)
+    bb = np.zeros((X, Y, Z), np.float64)
+
+    def splat(vol, p, sigma, amp):
+        lo = np.maximum(np.floor(p - 4 * sigma).astype(int), 0)
+        hi = np.minimum(np.ceil(p + 4 * sigma).astype(int) + 1, [X, Y, Z])
+        sl = tuple(slice(a, b) for a, b in zip(lo, hi))
+        d2 = (gx[sl] - p[0]) ** 2 + (gy[sl] - p[1]) ** 2 + (gz[sl] - p[2]) ** 2
+        np.maximum(vol[sl], amp * np.exp(-d2 / (2 * sigma * sigma)), out=vol[sl])
+
+    n_chains = len(n_residues)
+    for c, n in enumerate(n_residues):
+        x_lo, x_hi = 3 + c * (X - 6) / n_chains, 3 + (c + 1) * (X - 6) / n_chains - 12
+        lo = np.array([x_lo, wall_margin, wall_margin])
+        hi = np.array([max(x_hi, x_lo + 6), Y - 1.0 - wall_margin, Z - 1.0 - wall_margin])
+        pos = lo + rng.random(3) * (hi - lo)
+        for _ in range(n):
+            step = rng.normal(size=3)
+            pos = pos + 3.8 * step / np.linalg.norm(step)
+            pos = np.where(pos < lo, 2 * lo - pos, pos)
+            pos = np.where(pos > hi, 2 * hi - pos, pos)
+            splat(ca, pos, 0.9, 0.55 + 0.44 * rng.random())
+            splat(bb, pos, 1.8, 0.95)
+    for _ in range(spurious):
+        p = np.array([X - 5.0, 4.0 + rng.random() * (Y - 8), 4.0 + rng.random() * (Z - 8)])
+        for _ in range(3):
+            splat(ca, p + rng.normal(scale=1.5, size=3), 1.2, 0.9)
+    ca = np.clip(ca + rng.normal(scale=0.01, size=ca.shape), 0.0, 1.0).astype(np.float32)
+    bb = np.clip(bb + rng.normal(scale=0.01, size=bb.shape), 0.0, 1.0).astype(np.float32)
+    aa = rng.random((20, X, Y, Z), dtype=np.float32) ** 4
+    aa /= aa.sum(axis=0, keepdims=True)
+    aa_pred = aa.argmax(axis=0).astype(np.float32)
+    return dict(carbon_alpha_probability=ca, backbone_probability=bb,
+                amino_acid_probability=aa.astype(np.float32), amino_acid_prediction=aa_pred)

@@ -19,6 +19,8 @@ sys.path.insert(0, ROOT)
 
 from oracle import ref_harness as rh          # noqa: E402
 from oracle import mica_oracle as orc         # noqa: E402
+from oracle import candidates_oracle as cand_orc   # noqa: E402
+from oracle import masks_oracle as mask_orc   # noqa: E402
 from mica_b200 import synthetic               # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
@@ -204,10 +206,97 @@ def golden_stitch():
           **{k: v for k, v in vols.items()})
 
 
+CANDIDATE_CASES = [dict(shape=(56, 44, 40), n_residues=(60, 25), seed=1, wall_margin=3.0),
+                   dict(shape=(40, 64, 48), n_residues=(30, 30, 20), seed=2, wall_margin=3.0),
+                   dict(shape=(70, 30, 34), n_residues=(90,), seed=3, wall_margin=0.0)]
+
+
+def golden_candidates():
+    """N1: the unmodified Solver.clustering (utils/modeler.py:762-899) on synthetic stitched volumes; the
+    inputs are regenerated from the recipe, the reference's outputs are stored."""
+    out = {}
+    for n, case in enumerate(CANDIDATE_CASES):
+        p = synthetic.synthetic_predictions(case['shape'], case['n_residues'], seed=case['seed'],
+                                            wall_margin=case['wall_margin'])
+        ca, bb = p['carbon_alpha_probability'], p['backbone_probability']
+        aa, ap = p['amino_acid_probability'], p['amino_acid_prediction']
+        r = rh.solver_clustering(ca, bb, aa, ap)
+        o = cand_orc.ca_candidates(ca, bb, aa, ap)
+        vp = o['points'][o['valid']]
+        sc = ca[vp[:, 0], vp[:, 1], vp[:, 2]]
+        assert len(np.unique(sc)) == len(sc), 'ties among the scores: the reference order is undefined'
+        for k in ('CA_cands', 'CA_cands_AAProb', 'CA_cands_AA', 'CAProb_clusted'):
+            assert np.array_equal(r[k], o[k]), (n, k)
+        d, nm, best = cand_orc.neighbor_scores(o['CA_cands'], bb)
+        assert np.array_equal(d, r['cand_self_dis']) and np.array_equal(nm, r['neigh_mat']) and best == r['best_neigh']
+        print(f'    case {n}: {len(o["points"])} points, {int(o["labels"].max()) + 1} clusters, '
+              f'{len(o["picks"])} picks, {int((~o["picks_kept"]).sum())} on the border')
+        out.update({f'c{n}_CA_cands': r['CA_cands'], f'c{n}_CA_cands_AAProb': r['CA_cands_AAProb'],
+                    f'c{n}_CA_cands_AA': r['CA_cands_AA'],
+                    f'c{n}_clusted_lin': np.flatnonzero(r['CAProb_clusted']).astype(np.int64),
+                    f'c{n}_labels': o['labels'].astype(np.int32), f'c{n}_picks': o['picks'],
+                    f'c{n}_ca_crc': np.float64(ca.astype(np.float64).sum()),
+                    f'c{n}_neigh_mat': r['neigh_mat'].astype(np.float64)})
+    _save('candidates.npz', n_cases=np.int64(len(CANDIDATE_CASES)), **out)
+
+
+def _mask_case():
+    shape = (40, 36, 32)                                             # (nz, ny, nx): z beyond nx-1 is mis-clamped (D7)
+    origin = (np.float32(-2.5), np.float32(3.25), np.float32(1.0))
+    st = synthetic.synthetic_structure(160, (32, 36, 40), seed=5, origin_xyz=origin, hetero_every=7, unknown_every=11)
+    return shape, origin, st
+
+
+def golden_label_masks():
+    """N3: the three unmodified mask generators on a non-cubic map."""
+    shape, origin, st = _mask_case()
+    with tempfile.TemporaryDirectory() as td:
+        mp, pp = os.path.join(td, 'norm.mrc'), os.path.join(td, 's.pdb')
+        rh._write_mrc(mp, np.zeros(shape, np.float32), (1, 1, 1), origin)
+        synthetic.write_pdb(pp, st)
+        bb, ca, aa = rh.label_masks(mp, pp)
+    pos = mask_orc.atom_positions(st['coords'], origin, shape)
+    names, resn = np.array(st['atom_names']), np.array(st['res_names'])
+    assert np.array_equal(bb, mask_orc.atom_class_mask(pos, np.isin(names, ['N', 'CA', 'C', 'O']), shape))
+    assert np.array_equal(ca, mask_orc.atom_class_mask(pos, names == 'CA', shape))
+    sel = [i for i in range(len(names)) if names[i] == 'CA' and resn[i] in mask_orc.AA_LABELS]
+    labs = [mask_orc.AA_LABELS[resn[i]] for i in sel]
+    assert np.array_equal(aa, mask_orc.amino_acid_mask(pos[sel], labs, shape))
+    assert np.array_equal(aa, mask_orc.amino_acid_mask_closed_form(pos[sel], labs, shape))
+    _save('label_masks.npz', backbone=bb.astype(np.int8), carbon_alpha=ca.astype(np.int8), amino_acid=aa.astype(np.int8))
+
+
+def golden_docking_masks():
+    """N4: initial_map_processing + subsequent_map_processing, isotropic and anisotropic voxels."""
+    shape, origin, _ = _mask_case()
+    src = synthetic.synthetic_map(shape, seed=3)
+    out = {}
+    with tempfile.TemporaryDirectory() as td:
+        pp = os.path.join(td, 's.pdb')
+        for n, (vox, radius) in enumerate([((1.0, 1.0, 1.0), 2.0), ((1.06, 0.93, 1.2), 3.3), ((0.83, 0.83, 0.83), 2.0),
+                                           ((0.5, 0.5, 0.5), 2.0)]):
+            box = (31 * vox[0], 35 * vox[1], 31 * vox[2])
+            st = synthetic.synthetic_structure(120, box, seed=5, origin_xyz=origin, hetero_every=7)
+            synthetic.write_pdb(pp, st)
+            thr, masked, vs = rh.docking_masks(src, vox, origin, pp, td, 0.1, radius=radius)
+            o_thr = mask_orc.contour_threshold(src, 0.1)
+            sel = mask_orc.select_central_atoms(st['coords'])
+            assert np.array_equal(thr, o_thr)
+            assert np.array_equal(masked, mask_orc.mask_around_atoms(o_thr, sel, vs, origin, radius))
+            assert np.array_equal(masked, mask_orc.mask_around_atoms_restated(o_thr, sel, vs, origin, radius))
+            out.update({f'd{n}_voxel': np.array(vs, np.float32), f'd{n}_box': np.array(box), f'd{n}_radius': np.float64(radius),
+                        f'd{n}_zeroed': np.flatnonzero(masked != thr).astype(np.int64)})
+    _save('docking_masks.npz', n_cases=np.int64(4), thr_nonzero=np.flatnonzero(o_thr).astype(np.int64), **out)
+
+
 def main():
     assert rh.available(), 'needs /root/reference'
     os.makedirs(GOLDEN, exist_ok=True)
-    for fn in (golden_preprocess, golden_af3_cubic, golden_cubes, golden_training_twins, golden_stitch):
+    only = sys.argv[1:]
+    for fn in (golden_preprocess, golden_af3_cubic, golden_cubes, golden_training_twins, golden_stitch,
+               golden_candidates, golden_label_masks, golden_docking_masks):
+        if only and fn.__name__ not in only:
+            continue
         print(fn.__name__)
         fn()
 

@@ -195,3 +195,75 @@ def predict_and_stitch(grids_path, output_path, logits_for_cube, batch_threshold
         assert pr.run_inference(loader)
         ok, vols = pr.reconstruct_and_save_volumes()
     return ok, vols
+
+
+# ---------------------------------------------------------------------------------------
+# N1 (Solver.clustering head), N3 (label masks), N4 (docking masks)
+# ---------------------------------------------------------------------------------------
+def solver_clustering(ca_prob, bb_prob, aa_prob, aa_pred, ca_score_thrh=0.3, cluster_eps=10,
+                      cluster_min_points=10, nms_radius=9):
+    """``Solver.clustering`` (utils/modeler.py:762-899), unmodified, on in-memory volumes.
+
+    The method is called unbound on a bare namespace carrying exactly the attributes it reads
+    (the Solver constructor needs a full modelling configuration, FASTA files and Phenix).
+    ``open3d`` is absent: DBSCAN comes from oracle/standins/open3d (scikit-learn).  Returns a
+    dict with every intermediate the reference leaves behind."""
+    import logging
+    import types
+    _setup_path()
+    if _STANDINS not in sys.path:                    # open3d / superpose3d stand-ins
+        sys.path.insert(0, _STANDINS)
+    import utils.modeler as modeler
+    log = logging.getLogger('ref_harness.clustering')
+    log.disabled = True
+    s = types.SimpleNamespace(
+        logger=log, cluster_eps=cluster_eps, cluster_min_points=cluster_min_points, nms_radius=nms_radius,
+        modeling_config=types.SimpleNamespace(CA_score_thrh=ca_score_thrh),
+        CAProb=ca_prob, AAPred=aa_pred, neighbors2to6=[], neighbors0to6=[], neighbors0to7=[], neighbors2to7=[])
+    modeler.NNPred.BBProb, modeler.NNPred.AAProb = bb_prob, aa_prob
+    with _quiet():
+        modeler.Solver.clustering(s)
+    return dict(CA_cands=s.CA_cands, CA_cands_AAProb=s.CA_cands_AAProb, CA_cands_AA=s.CA_cands_AA,
+                CAProb_clusted=modeler.NNPred.CAProb_clusted, cand_self_dis=s.cand_self_dis,
+                neigh_mat=s.neigh_mat, best_neigh=[list(map(int, b)) for b in s.best_neigh],
+                neighbors2to6=[np.asarray(v) for v in s.neighbors2to6])
+
+
+def label_masks(normalized_map_path, pdb_path):
+    """scripts_for_training_data/create_{backbone,carbon_alpha,amino_acid}_mask.py
+    ``generate_mask`` (:120-177, :120-177, :128-183), unmodified.  Returns three int32 volumes."""
+    _setup_path()
+    sys.path.insert(0, os.path.join(REFERENCE_ROOT, 'scripts_for_training_data'))
+    import create_backbone_mask as mb
+    import create_carbon_alpha_mask as mc
+    import create_amino_acid_mask as ma
+    with _quiet():
+        return (mb.BackboneMask(normalized_map_path).generate_mask(pdb_path),
+                mc.CarbonAlphaMask(normalized_map_path).generate_mask(pdb_path),
+                ma.AminoAcidMaskGenerator(normalized_map_path).generate_mask(pdb_path))
+
+
+def docking_masks(src, voxel_xyz, origin_xyz, pdb_path, workdir, contour_level, radius=2.0, percentage=40,
+                  centroid_method='median'):
+    """``PhenixDockingProcessor.initial_map_processing`` then ``subsequent_map_processing``
+    (utils/dock_in_map.py:248-283, 285-364), unmodified, called unbound (the constructor wants a
+    Phenix installation).  Returns (thresholded map, masked map, voxel size as stored) read back from the MRCs."""
+    import logging
+    import types
+    _setup_path()
+    from utils.dock_in_map import PhenixDockingProcessor as P
+    log = logging.getLogger('ref_harness.docking')
+    log.disabled = True
+    me = types.SimpleNamespace(logger=log)
+    inp = os.path.join(workdir, 'dock_in.mrc')
+    thr = os.path.join(workdir, 'dock_thr.mrc')
+    out = os.path.join(workdir, 'dock_masked.mrc')
+    _write_mrc(inp, src, voxel_xyz, origin_xyz)
+    with _quiet():
+        P.initial_map_processing(me, inp, thr, contour_level)
+        P.subsequent_map_processing(me, thr, pdb_path, out, radius=radius, percentage=percentage,
+                                    centroid_method=centroid_method)
+    import mrcfile
+    with mrcfile.open(thr) as m:                     # what the reference saw: cella / m{x,y,z} in float32
+        vs = (np.float32(m.voxel_size.x), np.float32(m.voxel_size.y), np.float32(m.voxel_size.z))
+    return _read_mrc(thr), _read_mrc(out), vs

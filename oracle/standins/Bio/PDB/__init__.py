@@ -1,64 +1,7 @@
-"""Minimal stand-in for ``Bio.PDB`` used ONLY by oracle/ref_harness.py to run the
-unmodified reference (utils/preprocessing.py:52-53,269,275-298).  Fixed-column
-ATOM/HETATM parser: coordinates float32 from columns 31-38/39-46/47-54, atom
-name = columns 13-16 stripped, residue name = columns 18-20, hetero flag ' '
-for ATOM records."""
-import numpy as np
+"""Minimal stand-in for ``Bio.PDB`` (see _impl.py), used ONLY by oracle/ref_harness.py.  Laid out like
+Biopython: the parser class lives in the submodule ``Bio.PDB.PDBParser`` (utils/modeler.py:19 imports it
+by that path) and is re-exported here (``from Bio.PDB import *`` in the training scripts)."""
+from ._impl import PDBIO, _Atom, _Residue, _Structure  # noqa: F401
+from .PDBParser import PDBParser  # noqa: F401  (rebinds the name from the submodule to the class)
 
-
-class _Atom:
-    def __init__(self, name, coord):
-        self._name, self._coord = name, coord
-
-    def get_coord(self):
-        return self._coord
-
-    def get_name(self):
-        return self._name
-
-
-class _Residue(list):
-    def __init__(self, rid, resname):
-        super().__init__()
-        self._id, self._resname = rid, resname
-
-    def get_id(self):
-        return self._id
-
-    def get_resname(self):
-        return self._resname
-
-
-class PDBParser:
-    def __init__(self, QUIET=False, **kw):
-        pass
-
-    def get_structure(self, name, path):
-        models, chains, cur_res_key = [], None, None
-        with open(path) as f:
-            for line in f:
-                rec = line[:6]
-                if rec.startswith('MODEL') or chains is None:
-                    chains = {}
-                    models.append(chains)
-                    cur_res_key = None
-                    if rec.startswith('MODEL'):
-                        continue
-                if rec not in ('ATOM  ', 'HETATM'):
-                    continue
-                chain_id = line[21]
-                resname = line[17:20].strip()
-                resseq, icode = int(line[22:26]), line[26]
-                het = ' ' if rec == 'ATOM  ' else ('W' if resname in ('HOH', 'WAT') else 'H_' + resname)
-                key = (chain_id, het, resseq, icode)
-                chain = chains.setdefault(chain_id, [])
-                if key != cur_res_key:
-                    chain.append(_Residue((het, resseq, icode), resname))
-                    cur_res_key = key
-                coord = np.array([float(line[30:38]), float(line[38:46]), float(line[46:54])], 'f')
-                chain[-1].append(_Atom(line[12:16].strip(), coord))
-        return [list(m.values()) for m in models]
-
-
-class PDBIO:
-    pass
+__all__ = ['PDBParser', 'PDBIO']

@@ -59,10 +59,13 @@ class _Mrc:
 
     @voxel_size.setter
     def voxel_size(self, size):
-        try:
-            sx, sy, sz = size
-        except TypeError:
-            sx = sy = sz = size
+        if getattr(getattr(size, 'dtype', None), 'names', None):      # the (x, y, z) record voxel_size returns
+            sx, sy, sz = size['x'], size['y'], size['z']
+        else:
+            try:
+                sx, sy, sz = size
+            except TypeError:
+                sx = sy = sz = size
         h = self.header
         h.cella.x, h.cella.y, h.cella.z = sx * h.mx, sy * h.my, sz * h.mz
 
