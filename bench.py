@@ -357,6 +357,24 @@ def run_ours(args):
                    'copied out on side streams while later cube batches run); '
                    'host wall clock between device synchronisations, max over ranks'}
 
+    # the same call with amino_acid_probability (20 of the 23 channels) left in HBM: what the drop-in for the
+    # head of Solver.clustering (mica_b200/candidates.py) makes possible -- its only consumer in
+    # the reference (utils/modeler.py:850) then runs on the device.  Reported next to e2e, never instead of it.
+    e2e3 = None
+    if world == 1:
+        out3 = {k: v for k, v in out_host.items() if k != 'amino_acid_probability'}
+        run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out3, dev_vols)
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            _, h2d3, d2h3 = run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out3, dev_vols)
+        sync()
+        dt3 = (time.perf_counter() - t0) / args.e2e_steps
+        e2e3 = {'value': n_vox / dt3 / 1e9, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d3), 'd2h_bytes_per_step': int(d2h3),
+                'ms_per_step': dt3 * 1e3,
+                'note': 'as e2e, but amino_acid_probability stays on the device for mica_b200.candidates '
+                        '(utils/modeler.py:767-860 on the GPU); backbone / C-alpha / amino_acid_prediction go to the host'}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -423,6 +441,7 @@ def run_ours(args):
         },
         'af3_mode': args.af3_mode, 'variant': variant,
         'clocks': clk, 'gpu_launches': int(launches), 'host_enqueue_ms_per_step': host_ms, 'host_loop_enqueue_ms': getattr(pipe, 'last_loop_enqueue_ms', None), 'e2e': e2e,
+        'e2e_aa_prob_resident': e2e3,
     }
     if world == 1 and not args.no_cpu_baseline:
         line['cpu_baseline'], _ = cpu_baseline(args)

@@ -216,8 +216,9 @@ def clustering_head(solver, nnpred=None, volumes=None, labels_fn=None):
     ``CA_cands_AA`` and, when ``nnpred`` is given, ``NNPred.CAProb_clusted``).  ``volumes`` defaults to the
     device-resident volumes the predictor registered for ``modeling_config.output_path``."""
     if volumes is None:
+        import os
         from . import session
-        reg = session.get(('stitched', str(solver.modeling_config.output_path)))
+        reg = session.get(os.path.join(str(solver.modeling_config.output_path), 'results', 'device_volumes'))
         if reg is None:
             volumes = {'carbon_alpha_probability': solver.CAProb, 'backbone_probability': nnpred.BBProb,
                        'amino_acid_probability': nnpred.AAProb, 'amino_acid_prediction': solver.AAPred}

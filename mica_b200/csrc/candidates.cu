@@ -383,28 +383,27 @@ __device__ __forceinline__ void lin_to_xyz(long long l, const Lattice& g, int& x
 }
 
 // calls f(xx, yy, word_index_in_row, bits) for every non-empty 32-bit word of `bitvol` inside the ball;
-// f returns true to stop early
+// f returns true to stop early.  The (dx,dy) columns of the ball are visited first, first+step, ... so that
+// the lanes of a warp can share one point (first = lane, step = 32) or a thread can own it (0, 1).
 template <class F>
 __device__ __forceinline__ void for_ball_words(const uint32_t* __restrict__ bitvol, const Lattice& g, int x, int y,
-                                               int z, int R, int eps2, F f) {
-  for (int dx = -R; dx <= R; ++dx) {
-    const int xx = x + dx;
-    if (xx < 0 || xx >= g.X) continue;
-    for (int dy = -R; dy <= R; ++dy) {
-      const int yy = y + dy;
-      const int rem = eps2 - dx * dx - dy * dy;
-      if (yy < 0 || yy >= g.Y || rem < 0) continue;
-      const int hz = isqrt_floor(rem);
-      const int z0 = max(0, z - hz), z1 = min(g.Z - 1, z + hz);
-      const uint32_t* row = bitvol + ((long long)xx * g.Y + yy) * g.Wz;
-      const int w0 = z0 >> 5, w1 = z1 >> 5;
-      for (int w = w0; w <= w1; ++w) {
-        uint32_t mask = 0xffffffffu;
-        if (w == w0) mask &= 0xffffffffu << (z0 & 31);
-        if (w == w1) mask &= 0xffffffffu >> (31 - (z1 & 31));
-        const uint32_t bits = row[w] & mask;
-        if (bits && f(xx, yy, w, bits)) return;
-      }
+                                               int z, int R, int eps2, int first, int step, F f) {
+  const int side = 2 * R + 1;
+  for (int t = first; t < side * side; t += step) {
+    const int dx = t / side - R, dy = t % side - R;
+    const int xx = x + dx, yy = y + dy;
+    const int rem = eps2 - dx * dx - dy * dy;
+    if (xx < 0 || xx >= g.X || yy < 0 || yy >= g.Y || rem < 0) continue;
+    const int hz = isqrt_floor(rem);
+    const int z0 = max(0, z - hz), z1 = min(g.Z - 1, z + hz);
+    const uint32_t* row = bitvol + ((long long)xx * g.Y + yy) * g.Wz;
+    const int w0 = z0 >> 5, w1 = z1 >> 5;
+    for (int w = w0; w <= w1; ++w) {
+      uint32_t mask = 0xffffffffu;
+      if (w == w0) mask &= 0xffffffffu << (z0 & 31);
+      if (w == w1) mask &= 0xffffffffu >> (31 - (z1 & 31));
+      const uint32_t bits = row[w] & mask;
+      if (bits && f(xx, yy, w, bits)) return;
     }
   }
 }
@@ -429,7 +428,7 @@ dbscan_core_kernel(const long long* __restrict__ lin, long long n, Lattice g, co
   int x, y, z;
   lin_to_xyz(lin[i], g, x, y, z);
   int count = 0;
-  for_ball_words(occ, g, x, y, z, R, eps2, [&](int, int, int, uint32_t bits) {
+  for_ball_words(occ, g, x, y, z, R, eps2, 0, 1, [&](int, int, int, uint32_t bits) {
     count += __popc(bits);
     return count >= min_points;
   });
@@ -448,35 +447,57 @@ __device__ __forceinline__ int uf_find(const int32_t* parent, int i) {
   return i;
 }
 
-__device__ __forceinline__ void uf_union(int32_t* parent, int a, int b) {
-  while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
-    if (a == b) return;
+// find with path halving: every visited node is re-pointed to its grandparent.  Racing writers only ever
+// store an ancestor (a hooked root never becomes a root again and hooks go to smaller indices), so the
+// forest stays valid; roots themselves are written by atomicCAS only.
+__device__ __forceinline__ int uf_find_compress(int32_t* parent, int i) {
+  volatile int32_t* p = parent;
+  int q = p[i];
+  while (q != i) {
+    const int g = p[q];
+    if (g != q) p[i] = g;
+    i = q;
+    q = g;
+  }
+  return i;
+}
+
+// merges the trees of roots a and b; returns the root of the merged tree (the smaller index)
+__device__ __forceinline__ int uf_union_roots(int32_t* parent, int a, int b) {
+  while (a != b) {
     if (a < b) {
       const int t = a;
       a = b;
       b = t;
     }
     // a > b: hang root a under the smaller root b; roots only ever point to smaller indices
-    if (atomicCAS(&parent[a], a, b) == a) return;
+    const int old = atomicCAS(&parent[a], a, b);
+    if (old == a) return b;
+    a = uf_find_compress(parent, old);  // somebody else hooked a meanwhile: continue from its new root
+    b = uf_find_compress(parent, b);
   }
+  return a;
 }
 
+// one warp per core point: the lanes take the (dx,dy) columns of its ball in turn
 __global__ void __launch_bounds__(256)
 dbscan_union_kernel(const long long* __restrict__ lin, long long n, Lattice g, const uint32_t* __restrict__ coreocc,
                     const int32_t* __restrict__ slot, const uint8_t* __restrict__ is_core, int R, int eps2,
                     int32_t* parent) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (i >= n || !is_core[i]) return;
   int x, y, z;
   lin_to_xyz(lin[i], g, x, y, z);
-  for_ball_words(coreocc, g, x, y, z, R, eps2, [&](int xx, int yy, int w, uint32_t bits) {
+  int my_root = uf_find_compress(parent, (int)i);
+  for_ball_words(coreocc, g, x, y, z, R, eps2, lane, 32, [&](int xx, int yy, int w, uint32_t bits) {
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
       const int j = slot[((long long)xx * g.Y + yy) * g.Z + (w * 32 + b)];
-      if (j >= 0 && j < (int)i) uf_union(parent, (int)i, j);  // each pair once, from its higher index
+      if (j < 0 || j >= (int)i) continue;  // each pair once, from its higher index
+      const int rj = uf_find_compress(parent, j);
+      if (rj != my_root) my_root = uf_union_roots(parent, uf_find_compress(parent, my_root), rj);
     }
     return false;
   });
@@ -498,7 +519,7 @@ dbscan_root_kernel(const long long* __restrict__ lin, long long n, Lattice g, co
   int x, y, z;
   lin_to_xyz(lin[i], g, x, y, z);
   int best = 0x7fffffff;
-  for_ball_words(coreocc, g, x, y, z, R, eps2, [&](int xx, int yy, int w, uint32_t bits) {
+  for_ball_words(coreocc, g, x, y, z, R, eps2, 0, 1, [&](int xx, int yy, int w, uint32_t bits) {
     while (bits) {
       const int b = __ffs(bits) - 1;
       bits &= bits - 1;
@@ -754,7 +775,7 @@ extern "C" int mica_dbscan_lattice(const int64_t* lin, int64_t n, int X, int Y, 
   MICA_LAUNCH_CHECK("dbscan_mark_kernel");
   dbscan_core_kernel<<<grid, 256, 0, st>>>(l, n, g, occ, R, eps_sq, min_points, is_core, coreocc);
   MICA_LAUNCH_CHECK("dbscan_core_kernel");
-  dbscan_union_kernel<<<grid, 256, 0, st>>>(l, n, g, coreocc, slot, is_core, R, eps_sq, parent);
+  dbscan_union_kernel<<<grid_for(n * 32, 256), 256, 0, st>>>(l, n, g, coreocc, slot, is_core, R, eps_sq, parent);
   MICA_LAUNCH_CHECK("dbscan_union_kernel");
   dbscan_root_kernel<<<grid, 256, 0, st>>>(l, n, g, coreocc, slot, is_core, R, eps_sq, parent, root_of, is_root);
   MICA_LAUNCH_CHECK("dbscan_root_kernel");

@@ -390,6 +390,8 @@ class _SlabDrain:
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.pipe.device))
         for k, v in vols.as_dict().items():
+            if k not in self.out:                  # a volume the caller keeps on the device (e.g. the 20-channel
+                continue                           # amino_acid_probability when candidates.py consumes it there)
             dst = self.out[k]
             parts = [(dst[x0:layer_end], v[x0:layer_end])] if v.dim() == 3 else \
                     [(dst[c, x0:layer_end], v[c, x0:layer_end]) for c in range(v.shape[0])]

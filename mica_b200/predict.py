@@ -24,7 +24,14 @@ MAP_TYPES = ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_pre
 
 class CryoEMPredictor:
     def __init__(self, model_path, grids_path, output_path, save_output=True, device='cuda', quiet=False,
-                 model=None):
+                 model=None, keep_on_device=False, host_volumes=MAP_TYPES):
+        """``keep_on_device`` / ``host_volumes`` are additions to the reference signature: with
+        ``keep_on_device`` the stitched volumes stay registered in HBM (``session`` key
+        ``<output_path>/results/device_volumes``) for ``mica_b200.candidates.clustering_head``, and
+        ``host_volumes`` names the volumes copied to the host (default: all four, as the reference returns);
+        leaving out ``amino_acid_probability`` saves 20 of the 23 channels of PCIe traffic."""
+        self.keep_on_device = bool(keep_on_device)
+        self.host_volumes = tuple(host_volumes)
         self.model_path = model_path
         self.grids_path = grids_path
         self.output_path = output_path
@@ -205,13 +212,16 @@ class CryoEMPredictor:
             torch.cuda.synchronize()
             self.timing_stats['inference'] = time.time() - t0
             t0 = time.time()
-            volumes = {k: v.cpu().numpy() for k, v in vols.as_dict().items()}
+            if self.keep_on_device:
+                session.put(os.path.join(str(self.output_path), 'results', 'device_volumes'), **vols.as_dict())
+            volumes = {k: v.cpu().numpy() for k, v in vols.as_dict().items() if k in self.host_volumes}
             self.timing_stats['reconstruction'] = time.time() - t0
             if self.save_output:
                 t0 = time.time()
                 os.makedirs(self.reconstruction_path, exist_ok=True)
                 for k in MAP_TYPES:
-                    np.save(f'{self.reconstruction_path}/{k}.npy', volumes[k])
+                    if k in volumes:
+                        np.save(f'{self.reconstruction_path}/{k}.npy', volumes[k])
                 self.timing_stats['saving'] = time.time() - t0
             self.timing_stats['total'] = time.time() - t_total
             return True, volumes

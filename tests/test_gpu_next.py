@@ -279,3 +279,70 @@ def test_zero_around_atoms_edge_cases(cuda):
     assert int(status.item()) == 1
     thr = dm.contour_threshold(_dev(np.array([np.nan, 0.05, 0.1, 0.2, -1.0], np.float32), cuda), 0.1).cpu().numpy()
     assert np.isnan(thr[0]) and list(thr[1:]) == [0.0, np.float32(0.1), np.float32(0.2), 0.0]
+
+
+def test_predictor_keeps_volumes_resident_for_the_clustering_head(cuda, tmp_path):
+    """Solver.nnPred -> Solver.clustering without the 20-channel volume crossing PCIe: the predictor leaves
+    amino_acid_probability in HBM (keep_on_device, host_volumes) and clustering_head picks it up from the
+    session; results equal the oracle run on the predictor's full host output."""
+    from mica_b200 import candidates as cd, mrc, session
+    from mica_b200.create_grids import GridCreator
+    from mica_b200.predict import CryoEMPredictor
+    session.clear()
+    p = candidate_volumes(CANDIDATE_CASES[0])
+    X, Y, Z = p['carbon_alpha_probability'].shape
+
+    class Replay(torch.nn.Module):
+        """Stands where MICA stands: logits whose post-processing reproduces the synthetic volumes at the
+        cube cores (3-way softmax of (0, 0, log(2p/(1-p))) has p as its last entry)."""
+
+        def __init__(self, ijk, W, pad):
+            super().__init__()
+            self.ijk, self.W, self.pad, self.pos = ijk, W, pad, 0
+
+        def forward(self, x, af):
+            out = []
+            for b in range(x.shape[0]):
+                i, j, k = (int(v) - self.pad for v in self.ijk[self.pos + b])
+                def window(vol):
+                    w = np.zeros((self.W,) * 3, np.float32)
+                    xs, ys, zs = (slice(max(0, a), min(n, a + self.W)) for a, n in ((i, X), (j, Y), (k, Z)))
+                    w[xs.start - i:xs.stop - i, ys.start - j:ys.stop - j, zs.start - k:zs.stop - k] = vol[xs, ys, zs]
+                    return w
+                def two_way(prob):
+                    q = np.clip(window(prob), 1e-6, 1 - 1e-6).astype(np.float64)
+                    l3 = np.log(2 * q / (1 - q)).astype(np.float32)
+                    z = np.zeros_like(l3)
+                    return np.stack([z, z, z, l3])                 # classes 0, (dropped 1), 2, 3
+                aa = np.stack([np.zeros((self.W,) * 3, np.float32)] +
+                              [np.log(np.clip(window(p['amino_acid_probability'][c]), 1e-6, 1)) for c in range(20)])
+                out.append((two_way(p['backbone_probability']), two_way(p['carbon_alpha_probability']), aa))
+            self.pos += x.shape[0]
+            return tuple(torch.from_numpy(np.stack([o[t] for o in out])).to(x.device) for t in range(3))
+
+    norm_path = str(tmp_path / 'resampled_normalized_map.mrc')
+    mrc.write_mrc(norm_path, mrc.MrcMap(data=np.zeros((Z, Y, X), np.float32)))        # cube space is [x,y,z]
+    grids = str(tmp_path / 'grids' / 'ID') + '/'
+    r = GridCreator(quiet=True).create_normalized_map_grids(norm_path, os.path.join(grids, 'normalized_map_grids'))
+    assert r['success']
+    out_path = str(tmp_path / 'out')
+    pr = CryoEMPredictor('unused', grids, out_path, save_output=False, quiet=True, keep_on_device=True,
+                         host_volumes=('backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction'))
+    assert pr.select_processing_strategy()
+    pr.model = Replay(pr._source['ijk'], 64, 8)
+    ok, host = pr.run_prediction()
+    assert ok and set(host) == {'backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction'}
+    reg = session.get(os.path.join(out_path, 'results', 'device_volumes'))
+    assert reg is not None and reg['amino_acid_probability'].is_cuda and tuple(reg['amino_acid_probability'].shape) == (20, X, Y, Z)
+    full = {k: v.cpu().numpy() for k, v in reg.items()}
+    assert np.abs(full['carbon_alpha_probability'] - p['carbon_alpha_probability']).max() < 1e-4
+    solver = types.SimpleNamespace(cluster_eps=10, cluster_min_points=10, nms_radius=9,
+                                   modeling_config=types.SimpleNamespace(CA_score_thrh=0.3, output_path=out_path))
+    res = cd.clustering_head(solver)
+    o = co.ca_candidates(full['carbon_alpha_probability'], full['backbone_probability'], full['amino_acid_probability'],
+                         full['amino_acid_prediction'])
+    assert len(solver.CA_cands) > 20
+    assert np.array_equal(solver.CA_cands, o['CA_cands'])
+    assert np.array_equal(solver.CA_cands_AAProb, o['CA_cands_AAProb'])
+    assert np.array_equal(solver.CA_cands_AA, o['CA_cands_AA'])
+    session.clear()
