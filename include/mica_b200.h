@@ -286,6 +286,20 @@ int mica_cand_refine(const float* ca, const float* aa_prob, const float* aa_pred
                      const int64_t* pick_lin, int64_t m, double* out_xyz, float* out_aaprob, float* out_aa,
                      uint8_t* out_ok, mica_stream_t stream);
 
+/* utils/modeler.py:862-886 -- the rest of Solver.clustering: dis_out[a,b] = |c_a - c_b| (float64 [m,m], calc_dis
+ * :174-181) and neigh_out[a,b] = ((distance score) + (mean backbone probability at the four interior fifths of
+ * the segment)) / 2 for 2 <= dis <= 6, else 0 (float64 [m,m]); reproduces the reference's mixed float32 /
+ * float64 arithmetic (python float 1.0 + np.float32 stays float32).  xyz: device float64 [m,3]; m <= 65535. */
+int mica_cand_neighbor_graph(const double* xyz, int64_t m, const float* bb, int X, int Y, int Z, double* dis_out,
+                             double* neigh_out, mica_stream_t stream);
+/* :889-897 best[a] = (first, second): the two largest entries of row a of neigh (device int32 [m,2]; -1 where
+ * the entry is 0; equal scores: the higher index counts as larger, i.e. a stable ascending sort) */
+int mica_cand_best_neighbors(const double* neigh, int64_t m, int32_t* best, mica_stream_t stream);
+/* :866-873 per row of dis the ascending indices with dis <= max_dis: idx device int32 [m,cap], count device
+ * int32 [m] (count may exceed cap: call again with a larger cap) */
+int mica_cand_neighbor_lists(const double* dis, int64_t m, double max_dis, int cap, int32_t* idx, int32_t* count,
+                             mica_stream_t stream);
+
 /* ------------------------------------------------ N3: training label masks
  * scripts_for_training_data/create_backbone_mask.py:136-172, create_carbon_alpha_mask.py:136-173:
  * xyz device float32 [A,3] of ALL atoms in file order, is_class device uint8 [A]; mask device int32 [nz,ny,nx]

@@ -85,6 +85,9 @@ SIGNATURES = {
     'mica_cand_nms': (_i, [_p, _i, _i, _i, _p, _p, _i64, _i, _p, _p, C.POINTER(_i), _p]),
     'mica_cand_nms_picks': (_i, [_p, _i, _i, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
     'mica_cand_refine': (_i, [_p, _p, _p, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p]),
+    'mica_cand_neighbor_graph': (_i, [_p, _i64, _p, _i, _i, _i, _p, _p, _p]),
+    'mica_cand_best_neighbors': (_i, [_p, _i64, _p, _p]),
+    'mica_cand_neighbor_lists': (_i, [_p, _i64, C.c_double, _i, _p, _p, _p]),
     # N3: label masks, N4: docking masks
     'mica_label_class_mask': (_i, [_p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     'mica_label_aa_mask_workspace_bytes': (_sz, [_i, _i, _i]),

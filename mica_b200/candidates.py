@@ -195,7 +195,7 @@ def find_candidates(volumes, CA_score_thrh=0.3, cluster_eps=10, cluster_min_poin
             CA_cands_AA=out_aa.cpu().numpy()[kept],
             picks=pick_xyz.cpu().numpy().astype(np.int64), picks_kept=kept,
             n_points=n, n_clusters=n_labels, cluster_sums=sums32, cluster_avgs=avgs, nms_rounds=int(rounds.value),
-            device=dict(lin=lin, xyz=xyz, labels=labels, valid=valid, pick_lin=pick_lin))
+            device=dict(lin=lin, xyz=xyz, labels=labels, valid=valid, pick_lin=pick_lin, bb=bb))
         if want_clustered:                                                               # :800-802
             res['CAProb_clusted'] = clustered_volume(ca, lin, valid)
     return res
@@ -207,6 +207,69 @@ def clustered_volume(ca: torch.Tensor, lin: torch.Tensor, valid: torch.Tensor) -
     check(lib.mica_cand_clustered_volume(_dev(ca, torch.float32, 'ca'), ca.numel(), _ptr(lin), _ptr(valid),
                                          lin.shape[0], _ptr(out), _stream()), 'clustered_volume')
     return out
+
+
+def neighbor_graph(ca_cands, bb, device='cuda'):
+    """utils/modeler.py:862-897 for the refined picks ``ca_cands`` (float64 [m,3]) and the backbone volume
+    ``bb`` (device tensor or host array).  Returns dict(cand_self_dis, neigh_mat: float64 [m,m] host arrays;
+    neighbors2to6 / neighbors0to6 / neighbors0to7 / neighbors2to7: lists of index arrays; best_neigh: list of
+    lists) -- the attributes ``Solver.clustering`` leaves behind."""
+    ops.require_gpu()
+    dev = bb.device if isinstance(bb, torch.Tensor) and bb.is_cuda else torch.device(device)
+    bb = _as_device(bb, dev)
+    X, Y, Z = (int(s) for s in bb.shape)
+    ca_cands = np.ascontiguousarray(ca_cands, dtype=np.float64).reshape(-1, 3)
+    m = len(ca_cands)
+    if m < 2:
+        raise ValueError('not enough values to unpack (expected 2)')      # `second, first = ...argsort()[-2:]`
+    with torch.cuda.device(dev):
+        xyz = torch.from_numpy(ca_cands).to(dev)
+        dis = torch.empty((m, m), dtype=torch.float64, device=dev)
+        neigh = torch.empty((m, m), dtype=torch.float64, device=dev)
+        check(lib.mica_cand_neighbor_graph(_ptr(xyz), m, _ptr(bb), X, Y, Z, _ptr(dis), _ptr(neigh), _stream()),
+              'neighbor_graph')
+        best = torch.empty((m, 2), dtype=torch.int32, device=dev)
+        check(lib.mica_cand_best_neighbors(_ptr(neigh), m, _ptr(best), _stream()), 'best_neighbors')
+        cap = 64
+        while True:
+            idx = torch.empty((m, cap), dtype=torch.int32, device=dev)
+            cnt = torch.empty(m, dtype=torch.int32, device=dev)
+            check(lib.mica_cand_neighbor_lists(_ptr(dis), m, 7.0, cap, _ptr(idx), _ptr(cnt), _stream()),
+                  'neighbor_lists')
+            counts = cnt.cpu().numpy()
+            if int(counts.max()) <= cap:
+                break
+            cap = int(counts.max())
+        idx_h, dis_h, neigh_h = idx.cpu().numpy(), dis.cpu().numpy(), neigh.cpu().numpy()
+    mask = np.arange(cap)[None, :] < counts[:, None]
+    rows = np.broadcast_to(np.arange(m)[:, None], (m, cap))[mask]
+    cols = idx_h[mask].astype(np.int64)
+    d = dis_h[rows, cols]                                # distances of the listed (<= 7 A) pairs
+
+    def split(sel):                                      # per-row index arrays of the selected (row, col) pairs
+        per_row = np.bincount(rows[sel], minlength=m)
+        return np.split(cols[sel], np.cumsum(per_row)[:-1])
+
+    lists = dict(neighbors2to6=split((d <= 6) & (d >= 2)), neighbors0to6=split(d <= 6),      # :866-873
+                 neighbors0to7=split(np.ones(len(d), bool)), neighbors2to7=split(d >= 2))
+    best_h = best.cpu().numpy()
+    best_neigh = [[int(v) for v in row if v >= 0] for row in best_h]
+    return dict(cand_self_dis=dis_h, neigh_mat=neigh_h, best_neigh=best_neigh, **lists)
+
+
+def clustering(solver, nnpred=None, volumes=None, labels_fn=None):
+    """The whole of ``Solver.clustering`` (utils/modeler.py:762-899): ``clustering_head`` + the neighbour graph,
+    setting every attribute the reference method sets."""
+    res = clustering_head(solver, nnpred, volumes, labels_fn)
+    bb = res['device']['bb']
+    g = neighbor_graph(solver.CA_cands, bb)
+    solver.cand_self_dis, solver.neigh_mat, solver.best_neigh = g['cand_self_dis'], g['neigh_mat'], g['best_neigh']
+    for k in ('neighbors2to6', 'neighbors0to6', 'neighbors0to7', 'neighbors2to7'):
+        if isinstance(getattr(solver, k, None), list):
+            getattr(solver, k).extend(g[k])            # the reference appends to the lists Solver.__init__ made
+        else:
+            setattr(solver, k, g[k])
+    return res
 
 
 def clustering_head(solver, nnpred=None, volumes=None, labels_fn=None):

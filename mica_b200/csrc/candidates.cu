@@ -785,3 +785,149 @@ extern "C" int mica_dbscan_lattice(const int64_t* lin, int64_t n, int X, int Y, 
   MICA_LAUNCH_CHECK("dbscan_label_kernel");
   return MICA_OK;
 }
+
+// ==========================================================================================
+// utils/modeler.py:862-899 -- the neighbour graph of the picks (rest of Solver.clustering)
+// ==========================================================================================
+namespace mica {
+
+// cand_self_dis[a,b] = np.linalg.norm(c[a] - c[b]) (:862, calc_dis :174-181): sqrt((dx^2 + dy^2) + dz^2) in
+// float64; neigh_mat[a,b] (:875-886) for 2 <= dis <= 6, else 0.
+__global__ void __launch_bounds__(256)
+neighbor_graph_kernel(const double* __restrict__ xyz, long long m, const float* __restrict__ bb, int X, int Y, int Z,
+                      double* __restrict__ dis_out, double* __restrict__ neigh_out) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long a = blockIdx.y;
+  if (b >= m) return;
+  const double ax = xyz[3 * a], ay = xyz[3 * a + 1], az = xyz[3 * a + 2];
+  const double bx = xyz[3 * b], by = xyz[3 * b + 1], bz = xyz[3 * b + 2];
+  const double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  const double d = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+  dis_out[a * m + b] = d;
+  double score = 0.0;
+  if (d <= 6.0 && d >= 2.0) {
+    // BB_dens: float32 sum of the backbone probability at the four interior fifths of the segment a -> b
+    float dens = 0.f;
+#pragma unroll
+    for (int j = 1; j <= 4; ++j) {
+      const double wb = (double)j / 5.0, wa = (double)(5 - j) / 5.0;   // python: j/5, (5-j)/5
+      const long long cx = (long long)rint(__dadd_rn(__dmul_rn(wb, bx), __dmul_rn(wa, ax)));
+      const long long cy = (long long)rint(__dadd_rn(__dmul_rn(wb, by), __dmul_rn(wa, ay)));
+      const long long cz = (long long)rint(__dadd_rn(__dmul_rn(wb, bz), __dmul_rn(wa, az)));
+      const long long ix = cx < 0 ? cx + X : cx, iy = cy < 0 ? cy + Y : cy, iz = cz < 0 ? cz + Z : cz;  // numpy wrap
+      float v = 0.f;
+      if (ix >= 0 && ix < X && iy >= 0 && iy < Y && iz >= 0 && iz < Z) v = bb[(ix * Y + iy) * Z + iz];
+      dens = __fadd_rn(dens, v);
+    }
+    const float quarter = __fdiv_rn(dens, 4.0f);                      // BB_dens / 4 stays float32
+    const double t = __dsub_rn(fabs(__dsub_rn(d, 3.8)), 0.5);         // abs(dis - 3.8) - 0.5
+    if (t <= 0.0) {
+      // max(0, t) is the python int 0 -> dis_score is the python float 1.0 -> the sum is formed in FLOAT32
+      score = (double)__fdiv_rn(__fadd_rn(1.0f, quarter), 2.0f);
+    } else {
+      // np.float64 path: dis_score = max(0, 1 - t/2) (> 0 for every d in [2, 6])
+      const double ds = __dsub_rn(1.0, __ddiv_rn(t, 2.0));
+      score = ds > 0.0 ? __ddiv_rn(__dadd_rn(ds, (double)quarter), 2.0) : (double)__fdiv_rn(quarter, 2.0f);
+    }
+  }
+  neigh_out[a * m + b] = score;
+}
+
+// :889-897 -- the two best-scoring neighbours of every pick: best[a] = (first, second), -1 where the score is 0.
+// Ascending stable order semantics: among equal scores the higher index counts as larger.
+__global__ void __launch_bounds__(256)
+best_neighbors_kernel(const double* __restrict__ neigh, long long m, int32_t* __restrict__ best) {
+  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= m) return;
+  double v1 = -1.0, v2 = -1.0;  // scores are >= 0
+  int i1 = -1, i2 = -1;
+  const double* row = neigh + a * m;
+  for (long long b = lane; b < m; b += 32) {
+    const double v = row[b];
+    if (v > v1 || (v == v1 && (int)b > i1)) {
+      v2 = v1; i2 = i1; v1 = v; i1 = (int)b;
+    } else if (v > v2 || (v == v2 && (int)b > i2)) {
+      v2 = v; i2 = (int)b;
+    }
+  }
+  // merge the per-lane top-2 lists
+#pragma unroll
+  for (int d = 16; d >= 1; d >>= 1) {
+    const double o1 = __shfl_xor_sync(0xffffffffu, v1, d), o2 = __shfl_xor_sync(0xffffffffu, v2, d);
+    const int j1 = __shfl_xor_sync(0xffffffffu, i1, d), j2 = __shfl_xor_sync(0xffffffffu, i2, d);
+    double c[4] = {v1, v2, o1, o2};
+    int ci[4] = {i1, i2, j1, j2};
+    double n1 = -1.0, n2 = -1.0;
+    int k1 = -1, k2 = -1;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      if (ci[t] < 0 || ci[t] == k1 || ci[t] == k2) continue;
+      if (c[t] > n1 || (c[t] == n1 && ci[t] > k1)) {
+        n2 = n1; k2 = k1; n1 = c[t]; k1 = ci[t];
+      } else if (c[t] > n2 || (c[t] == n2 && ci[t] > k2)) {
+        n2 = c[t]; k2 = ci[t];
+      }
+    }
+    v1 = n1; v2 = n2; i1 = k1; i2 = k2;
+  }
+  if (lane == 0) {
+    best[2 * a + 0] = (i1 >= 0 && v1 != 0.0) ? i1 : -1;
+    best[2 * a + 1] = (i2 >= 0 && v2 != 0.0) ? i2 : -1;
+  }
+}
+
+// :866-873 -- per pick the ascending list of picks within max_dis (one warp per row, ballot-ordered append)
+__global__ void __launch_bounds__(256)
+neighbor_lists_kernel(const double* __restrict__ dis, long long m, double max_dis, int cap, int32_t* __restrict__ idx,
+                      int32_t* __restrict__ count) {
+  const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= m) return;
+  const double* row = dis + a * m;
+  int n = 0;
+  for (long long b0 = 0; b0 < m; b0 += 32) {
+    const long long b = b0 + lane;
+    const bool hit = b < m && row[b] <= max_dis;
+    const unsigned mask = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = n + __popc(mask & ((1u << lane) - 1u));
+      if (pos < cap) idx[a * cap + pos] = (int32_t)b;
+    }
+    n += __popc(mask);
+  }
+  if (lane == 0) count[a] = n;
+}
+
+}  // namespace mica
+
+extern "C" int mica_cand_neighbor_graph(const double* xyz, int64_t m, const float* bb, int X, int Y, int Z,
+                                        double* dis_out, double* neigh_out, mica_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m <= 0) return MICA_OK;
+  MICA_REQUIRE(xyz && bb && dis_out && neigh_out, "null pointer");
+  MICA_REQUIRE(X > 0 && Y > 0 && Z > 0 && m <= 65535, "bad arguments (at most 65535 picks)");
+  dim3 grid(grid_for(m, 256), (unsigned)m);
+  neighbor_graph_kernel<<<grid, 256, 0, st>>>(xyz, m, bb, X, Y, Z, dis_out, neigh_out);
+  MICA_LAUNCH_CHECK("neighbor_graph_kernel");
+  return MICA_OK;
+}
+
+extern "C" int mica_cand_best_neighbors(const double* neigh, int64_t m, int32_t* best, mica_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m <= 0) return MICA_OK;
+  MICA_REQUIRE(neigh && best, "null pointer");
+  best_neighbors_kernel<<<grid_for(m * 32, 256), 256, 0, st>>>(neigh, m, best);
+  MICA_LAUNCH_CHECK("best_neighbors_kernel");
+  return MICA_OK;
+}
+
+extern "C" int mica_cand_neighbor_lists(const double* dis, int64_t m, double max_dis, int cap, int32_t* idx,
+                                        int32_t* count, mica_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (m <= 0) return MICA_OK;
+  MICA_REQUIRE(dis && idx && count && cap > 0, "bad arguments");
+  neighbor_lists_kernel<<<grid_for(m * 32, 256), 256, 0, st>>>(dis, m, max_dis, cap, idx, count);
+  MICA_LAUNCH_CHECK("neighbor_lists_kernel");
+  return MICA_OK;
+}

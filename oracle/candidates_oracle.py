@@ -1,5 +1,5 @@
-"""CPU oracle for SURVEY.md section 8(f) row N1: the head of ``Solver.clustering``
-(utils/modeler.py:762-858) -- C-alpha candidates from the stitched volumes.
+"""CPU oracle for SURVEY.md section 8(f) row N1: ``Solver.clustering`` (utils/modeler.py:762-899) --
+C-alpha candidates from the stitched volumes (:767-860) and their neighbour graph (:862-899).
 
 TEST INFRASTRUCTURE ONLY (same rule as oracle/mica_oracle.py: nothing under ``mica_b200/``
 imports this; only tests/, smoke() and bench.py's CPU legs do, as the checker).
@@ -201,6 +201,11 @@ def neighbor_scores(ca_cands, bb_prob):
                 c = np.round(j / 5 * ca_cands[b] + (5 - j) / 5 * ca_cands[a]).astype(int)
                 dens += bb_prob[c[0], c[1], c[2]]
             neigh[a, b] = (dis_score + dens / 4) / 2
+    lists = dict(neighbors2to6=[np.where((dis[a] <= 6) * (dis[a] >= 2))[0] for a in range(m)],
+                 neighbors0to6=[np.where(dis[a] <= 6)[0] for a in range(m)],
+                 neighbors0to7=[np.where(dis[a] <= 7)[0] for a in range(m)],
+                 neighbors2to7=[np.where((dis[a] <= 7) * (dis[a] >= 2))[0] for a in range(m)])
+    neighbor_scores.lists = lists                        # :866-873 (kept as an attribute: callers unpack three)
     best = []
     for a in range(m):
         lst = []

@@ -229,6 +229,11 @@ def golden_candidates():
             assert np.array_equal(r[k], o[k]), (n, k)
         d, nm, best = cand_orc.neighbor_scores(o['CA_cands'], bb)
         assert np.array_equal(d, r['cand_self_dis']) and np.array_equal(nm, r['neigh_mat']) and best == r['best_neigh']
+        for key, lst in cand_orc.neighbor_scores.lists.items():
+            assert all(np.array_equal(x, y) for x, y in zip(lst, r[key])) and len(lst) == len(r[key]), key
+        for row in nm:                                   # the two best scores of a row must not tie (unstable argsort)
+            top = np.sort(row[row > 0])[-3:]
+            assert len(np.unique(top)) == len(top)
         print(f'    case {n}: {len(o["points"])} points, {int(o["labels"].max()) + 1} clusters, '
               f'{len(o["picks"])} picks, {int((~o["picks_kept"]).sum())} on the border')
         out.update({f'c{n}_CA_cands': r['CA_cands'], f'c{n}_CA_cands_AAProb': r['CA_cands_AAProb'],
@@ -236,7 +241,12 @@ def golden_candidates():
                     f'c{n}_clusted_lin': np.flatnonzero(r['CAProb_clusted']).astype(np.int64),
                     f'c{n}_labels': o['labels'].astype(np.int32), f'c{n}_picks': o['picks'],
                     f'c{n}_ca_crc': np.float64(ca.astype(np.float64).sum()),
-                    f'c{n}_neigh_mat': r['neigh_mat'].astype(np.float64)})
+                    f'c{n}_neigh_mat': r['neigh_mat'].astype(np.float64),
+                    f'c{n}_cand_self_dis': r['cand_self_dis'].astype(np.float64),
+                    f'c{n}_best_neigh': np.array([b + [-1] * (2 - len(b)) for b in r['best_neigh']], dtype=np.int32),
+                    **{f'c{n}_{key}_flat': np.concatenate(r[key]).astype(np.int32) for key in cand_orc.neighbor_scores.lists},
+                    **{f'c{n}_{key}_len': np.array([len(x) for x in r[key]], dtype=np.int32)
+                       for key in cand_orc.neighbor_scores.lists}})
     _save('candidates.npz', n_cases=np.int64(len(CANDIDATE_CASES)), **out)
 
 

@@ -226,7 +226,10 @@ def solver_clustering(ca_prob, bb_prob, aa_prob, aa_pred, ca_score_thrh=0.3, clu
     return dict(CA_cands=s.CA_cands, CA_cands_AAProb=s.CA_cands_AAProb, CA_cands_AA=s.CA_cands_AA,
                 CAProb_clusted=modeler.NNPred.CAProb_clusted, cand_self_dis=s.cand_self_dis,
                 neigh_mat=s.neigh_mat, best_neigh=[list(map(int, b)) for b in s.best_neigh],
-                neighbors2to6=[np.asarray(v) for v in s.neighbors2to6])
+                neighbors2to6=[np.asarray(v) for v in s.neighbors2to6],
+                neighbors0to6=[np.asarray(v) for v in s.neighbors0to6],
+                neighbors0to7=[np.asarray(v) for v in s.neighbors0to7],
+                neighbors2to7=[np.asarray(v) for v in s.neighbors2to7])
 
 
 def label_masks(normalized_map_path, pdb_path):

@@ -346,3 +346,59 @@ def test_predictor_keeps_volumes_resident_for_the_clustering_head(cuda, tmp_path
     assert np.array_equal(solver.CA_cands_AAProb, o['CA_cands_AAProb'])
     assert np.array_equal(solver.CA_cands_AA, o['CA_cands_AA'])
     session.clear()
+
+
+def _unflatten(g, prefix):
+    return np.split(g[prefix + '_flat'], np.cumsum(g[prefix + '_len'])[:-1])
+
+
+@pytest.mark.parametrize('n', range(len(CANDIDATE_CASES)))
+def test_neighbor_graph_matches_reference_golden(cuda, golden_dir, n):
+    """utils/modeler.py:862-899 (distance matrix, neighbour lists, neigh_mat, best_neigh), bit for bit --
+    including the reference's mixed float32/float64 score arithmetic."""
+    from mica_b200 import candidates as cd
+    g = np.load(os.path.join(golden_dir, 'candidates.npz'))
+    p = candidate_volumes(CANDIDATE_CASES[n])
+    res = cd.neighbor_graph(g[f'c{n}_CA_cands'], _dev(p['backbone_probability'], cuda))
+    assert np.array_equal(res['cand_self_dis'], g[f'c{n}_cand_self_dis'])
+    assert np.array_equal(res['neigh_mat'], g[f'c{n}_neigh_mat'])
+    want_best = [[int(v) for v in row if v >= 0] for row in g[f'c{n}_best_neigh']]
+    assert res['best_neigh'] == want_best
+    for key in ('neighbors2to6', 'neighbors0to6', 'neighbors0to7', 'neighbors2to7'):
+        want = _unflatten(g, f'c{n}_{key}')
+        assert len(want) == len(res[key]) and all(np.array_equal(a, b) for a, b in zip(res[key], want)), key
+
+
+def test_neighbor_graph_dense_points_and_whole_clustering(cuda):
+    from mica_b200 import candidates as cd
+    rng = np.random.default_rng(8)
+    shape = (30, 28, 26)
+    bb = rng.random(shape, dtype=np.float32)
+    pts = rng.random((700, 3)) * (np.array(shape) - 3) + 1.0              # ~100 points within 7 A: list regrowth
+    res = cd.neighbor_graph(pts, bb)
+    dis, nm, best = co.neighbor_scores(pts, bb)
+    assert np.array_equal(res['cand_self_dis'], dis) and np.array_equal(res['neigh_mat'], nm)
+    assert max(len(v) for v in res['neighbors0to7']) > 64
+    for key, want in co.neighbor_scores.lists.items():
+        assert all(np.array_equal(a, b) for a, b in zip(res[key], want)), key
+    for a, (got, want) in enumerate(zip(res['best_neigh'], best)):
+        row = nm[a]
+        top = np.sort(row[row > 0])[-3:]
+        if len(np.unique(top)) == len(top):                                # untied rows: the reference's order
+            assert got == want, a
+        else:                                    # ties (coarse float32 scores): same scores, stable choice of index
+            assert [row[j] for j in got] == [row[j] for j in want], a
+    # the whole method through the Solver-facing wrapper
+    p = candidate_volumes(CANDIDATE_CASES[1])
+    solver = types.SimpleNamespace(cluster_eps=10, cluster_min_points=10, nms_radius=9,
+                                   modeling_config=types.SimpleNamespace(CA_score_thrh=0.3, output_path='/nonexistent'),
+                                   CAProb=p['carbon_alpha_probability'], AAPred=p['amino_acid_prediction'],
+                                   neighbors2to6=[], neighbors0to6=[], neighbors0to7=[], neighbors2to7=[])
+    nnpred = types.SimpleNamespace(BBProb=p['backbone_probability'], AAProb=p['amino_acid_probability'])
+    cd.clustering(solver, nnpred)
+    o = co.ca_candidates(p['carbon_alpha_probability'], p['backbone_probability'], p['amino_acid_probability'],
+                         p['amino_acid_prediction'])
+    dis, nm, best = co.neighbor_scores(o['CA_cands'], p['backbone_probability'])
+    assert np.array_equal(solver.CA_cands, o['CA_cands']) and np.array_equal(solver.neigh_mat, nm)
+    assert np.array_equal(solver.cand_self_dis, dis) and solver.best_neigh == best
+    assert len(solver.neighbors2to6) == len(o['CA_cands'])

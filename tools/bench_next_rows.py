@@ -87,6 +87,16 @@ def main():
     res = cd.find_candidates(vols)
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    graph = cd.neighbor_graph(res['CA_cands'], vols['backbone_probability'])
+    graph_wall = (time.perf_counter() - t0) * 1e3
+    t0 = time.perf_counter()
+    graph = cd.neighbor_graph(res['CA_cands'], vols['backbone_probability'])
+    graph_wall = min(graph_wall, (time.perf_counter() - t0) * 1e3)
+    out['N1_neighbor_graph'] = {'picks': int(len(res['CA_cands'])), 'wall_ms_incl_two_dense_matrices_to_host': graph_wall,
+                                'matrix_bytes_to_host': int(graph['cand_self_dis'].nbytes + graph['neigh_mat'].nbytes),
+                                'scored_pairs': int((graph['neigh_mat'] > 0).sum())}
+    del graph
     out['N1_candidates'] = {
         'points_above_threshold': int(lin.shape[0]), 'clusters': int(ncl), 'picks': int(len(res['picks'])),
         'candidates': int(len(res['CA_cands'])), 'nms_rounds': int(res['nms_rounds']),
