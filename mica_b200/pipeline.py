@@ -125,7 +125,8 @@ class MapPipeline:
         #: caller's stream (two input buffers).  False = everything on the caller's stream.
         self.prefetch = True
         self._deferred = []
-        self._pre_stream = None
+        self._pinned_free = []          # (order-stats record, AF3 status word) pairs in pinned memory, reused:
+        self._pre_stream = None         # cudaHostAlloc synchronises the device, so never allocate per step
 
     # ------------------------------------------------------------------ stage 1+2
     def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
@@ -324,11 +325,12 @@ class MapPipeline:
         pending, self._deferred = self._deferred, []
         for rec, af, ev in pending:
             ev.synchronize()
+            self._pinned_free.append((rec, af))
             med, p, npos, status = ops.OrderStats.decode(rec)
             self.norm_status, self.median, self.p999, self.n_pos = status, med, p, npos
             if status != NORM_OK:
                 raise MicaError(f'normalisation failed (status {status})')
-            if af is not None and int(af[0]) != 0:
+            if af[1] and int(af[0]) != 0:
                 raise MicaError('AF3 encoding failed: atom index outside the grid (reference IndexError path, D7)')
 
     # ------------------------------------------------------------------ whole path
@@ -346,11 +348,14 @@ class MapPipeline:
             self.af3, self._atoms_binned = None, False
         vols = self.predict_and_stitch(model_fn, vols, on_batch)
         if defer_check:
-            rec = self.stats.result_async()
-            af = None
+            if self._pinned_free:
+                rec, af = self._pinned_free.pop()
+            else:
+                rec, af = torch.zeros(32, dtype=torch.uint8).pin_memory(), torch.zeros(2, dtype=torch.int32).pin_memory()
+            rec = self.stats.result_async(rec)
+            af[1] = 1 if atoms is not None else 0           # host-side flag: is af[0] meaningful for this step
             if atoms is not None:
-                af = torch.zeros(1, dtype=torch.int32).pin_memory()
-                af.copy_(self._af3_status, non_blocking=True)
+                af[:1].copy_(self._af3_status, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(self.device))
             self._deferred.append((rec, af, ev))
