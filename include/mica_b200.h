@@ -275,10 +275,11 @@ int mica_cand_clustered_volume(const float* ca, int64_t n_vox, const int64_t* li
 int mica_cand_nms(const float* ca, int X, int Y, int Z, const int64_t* lin, const uint8_t* valid, int64_t n,
                   int nms_radius_sq, float* work, int32_t* flag_dev, int* rounds_out, mica_stream_t stream);
 /* the picks in the reference's order (best probability first, ties by np.where order): sorted_lin device int64
- * [cap], sorted_xyz device int32 [cap,3]; scratch_* device [cap]; *n_picks_dev device int64 (the call
- * synchronises to read it and fails with MICA_ERR_WORKSPACE if it exceeds cap). */
+ * [cap], sorted_xyz device int32 [cap,3]; *n_picks_dev device int64 (the call synchronises to read it and fails
+ * with MICA_ERR_WORKSPACE if it exceeds cap).  Ordering is a bucketed rank count, not an m^2 comparison. */
+size_t mica_cand_picks_workspace_bytes(int64_t cap);
 int mica_cand_nms_picks(const float* work, int Y, int Z, const int64_t* lin, const uint8_t* valid, int64_t n,
-                        int64_t cap, int64_t* scratch_lin, float* scratch_p, int64_t* n_picks_dev,
+                        int64_t cap, void* workspace, size_t workspace_bytes, int64_t* n_picks_dev,
                         int64_t* sorted_lin, int32_t* sorted_xyz, mica_stream_t stream);
 /* :837-860 per pick: CA_cands (float64 [m,3]), CA_cands_AAProb rows (float32 [m,20]), CA_cands_AA
  * (float32 [m]) and ok (uint8 [m]; 0 = pick on the volume border, skipped by the reference's try/except). */

@@ -83,7 +83,8 @@ SIGNATURES = {
     'mica_cand_valid_points': (_i, [_p, _p, _i64, _i, _p, _p]),
     'mica_cand_clustered_volume': (_i, [_p, _i64, _p, _p, _i64, _p, _p]),
     'mica_cand_nms': (_i, [_p, _i, _i, _i, _p, _p, _i64, _i, _p, _p, C.POINTER(_i), _p]),
-    'mica_cand_nms_picks': (_i, [_p, _i, _i, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _p]),
+    'mica_cand_picks_workspace_bytes': (_sz, [_i64]),
+    'mica_cand_nms_picks': (_i, [_p, _i, _i, _p, _p, _i64, _i64, _p, _sz, _p, _p, _p, _p]),
     'mica_cand_refine': (_i, [_p, _p, _p, _i, _i, _i, _p, _i64, _p, _p, _p, _p, _p]),
     'mica_cand_neighbor_graph': (_i, [_p, _i64, _p, _i, _i, _i, _p, _p, _p]),
     'mica_cand_best_neighbors': (_i, [_p, _i64, _p, _p]),

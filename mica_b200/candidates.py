@@ -171,14 +171,13 @@ def find_candidates(volumes, CA_score_thrh=0.3, cluster_eps=10, cluster_min_poin
         check(lib.mica_cand_nms(_ptr(ca), X, Y, Z, _ptr(lin), _ptr(valid), n, int(nms_radius), _ptr(work),
                                 _ptr(flag), C.byref(rounds), _stream()), 'nms')
         cap = n
-        scratch_lin = torch.empty(cap, dtype=torch.int64, device=dev)
-        scratch_p = torch.empty(cap, dtype=torch.float32, device=dev)
+        ws_bytes = lib.mica_cand_picks_workspace_bytes(cap)
+        picks_ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         pick_lin = torch.empty(cap, dtype=torch.int64, device=dev)
         pick_xyz = torch.empty((cap, 3), dtype=torch.int32, device=dev)
         n_picks = torch.zeros(1, dtype=torch.int64, device=dev)
-        check(lib.mica_cand_nms_picks(_ptr(work), Y, Z, _ptr(lin), _ptr(valid), n, cap, _ptr(scratch_lin),
-                                      _ptr(scratch_p), _ptr(n_picks), _ptr(pick_lin), _ptr(pick_xyz), _stream()),
-              'nms_picks')
+        check(lib.mica_cand_nms_picks(_ptr(work), Y, Z, _ptr(lin), _ptr(valid), n, cap, _ptr(picks_ws), ws_bytes,
+                                      _ptr(n_picks), _ptr(pick_lin), _ptr(pick_xyz), _stream()), 'nms_picks')
         m = _scalar_i64(n_picks)
         pick_lin, pick_xyz = pick_lin[:m], pick_xyz[:m]
         # :837-860

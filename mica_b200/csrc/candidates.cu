@@ -254,18 +254,49 @@ nms_collect_kernel(const float* __restrict__ w, const long long* __restrict__ li
   }
 }
 
-// rank sort of the picks: position = number of picks with higher priority
+// Order of the picks = the reference's argsort(-p): rank = number of picks with higher priority (higher p, ties by
+// lower linear index).  Counting over all pairs would be m^2; instead the picks are bucketed by the top bits of p
+// (descending), a scan gives each bucket its first rank, and the count runs inside the pick's own bucket only.
+constexpr int kRankBuckets = 1 << 16;
+__device__ __forceinline__ int rank_bucket(float p) {
+  const uint32_t one = 0x3F800000u, bits = __float_as_uint(p);  // p > 0: the bit pattern is monotone in p
+  if (bits >= one) return 0;
+  const uint32_t b = (one - bits) >> 9;
+  return b < (uint32_t)kRankBuckets ? (int)b : kRankBuckets - 1;
+}
+
 __global__ void __launch_bounds__(256)
-nms_rank_kernel(const long long* __restrict__ picked_lin, const float* __restrict__ picked_p, long long m,
-                int Y, int Z, long long* __restrict__ sorted_lin, int32_t* __restrict__ sorted_xyz) {
+nms_bucket_count_kernel(const float* __restrict__ picked_p, long long m, uint32_t* __restrict__ counts) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < m) atomicAdd(&counts[rank_bucket(picked_p[a])], 1u);
+}
+
+__global__ void __launch_bounds__(256)
+nms_bucket_scatter_kernel(const long long* __restrict__ picked_lin, const float* __restrict__ picked_p, long long m,
+                          const long long* __restrict__ bucket_first, uint32_t* __restrict__ fill,
+                          long long* __restrict__ by_bucket_lin, float* __restrict__ by_bucket_p) {
   const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= m) return;
-  const float p = picked_p[a];
-  const long long l = picked_lin[a];
-  long long rank = 0;
-  for (long long b = 0; b < m; ++b) {
-    const float q = picked_p[b];
-    rank += (q > p || (q == p && picked_lin[b] < l)) ? 1 : 0;
+  const int b = rank_bucket(picked_p[a]);
+  const long long pos = bucket_first[b] + atomicAdd(&fill[b], 1u);
+  by_bucket_lin[pos] = picked_lin[a];
+  by_bucket_p[pos] = picked_p[a];
+}
+
+__global__ void __launch_bounds__(256)
+nms_rank_kernel(const long long* __restrict__ by_bucket_lin, const float* __restrict__ by_bucket_p, long long m,
+                const long long* __restrict__ bucket_first, const uint32_t* __restrict__ counts, int Y, int Z,
+                long long* __restrict__ sorted_lin, int32_t* __restrict__ sorted_xyz) {
+  const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  const float p = by_bucket_p[a];
+  const long long l = by_bucket_lin[a];
+  const int bkt = rank_bucket(p);
+  const long long first = bucket_first[bkt], last = first + counts[bkt];
+  long long rank = first;
+  for (long long b = first; b < last; ++b) {
+    const float q = by_bucket_p[b];
+    rank += (q > p || (q == p && by_bucket_lin[b] < l)) ? 1 : 0;
   }
   sorted_lin[rank] = l;
   const long long xy = l / Z;
@@ -673,26 +704,50 @@ extern "C" int mica_cand_nms(const float* ca, int X, int Y, int Z, const int64_t
   return MICA_OK;
 }
 
-/* picks in the reference's order (best probability first).  picked_lin/picked_p: scratch of `cap` entries. */
+extern "C" size_t mica_cand_picks_workspace_bytes(int64_t cap) {
+  const size_t c = (size_t)(cap > 0 ? cap : 1);
+  return align256(kRankBuckets * sizeof(uint32_t)) * 2 + align256(kRankBuckets * sizeof(long long)) +
+         2 * (align256(c * sizeof(long long)) + align256(c * sizeof(float)));
+}
+
+/* picks in the reference's order (best probability first).  workspace: mica_cand_picks_workspace_bytes(cap). */
 extern "C" int mica_cand_nms_picks(const float* work, int Y, int Z, const int64_t* lin, const uint8_t* valid,
-                                   int64_t n, int64_t cap, int64_t* scratch_lin, float* scratch_p,
+                                   int64_t n, int64_t cap, void* workspace, size_t workspace_bytes,
                                    int64_t* n_picks_dev, int64_t* sorted_lin, int32_t* sorted_xyz,
                                    mica_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   MICA_REQUIRE(work && n_picks_dev, "null pointer");
   MICA_CUDA(cudaMemsetAsync(n_picks_dev, 0, sizeof(int64_t), st));
   if (n <= 0 || cap <= 0) return MICA_OK;
-  MICA_REQUIRE(lin && valid && scratch_lin && scratch_p && sorted_lin && sorted_xyz, "null pointer");
-  nms_collect_kernel<<<grid_for(n, 256), 256, 0, st>>>(work, (const long long*)lin, valid, n, cap,
-                                                       (long long*)scratch_lin, scratch_p,
-                                                       (unsigned long long*)n_picks_dev);
+  MICA_REQUIRE(lin && valid && workspace && sorted_lin && sorted_xyz, "null pointer");
+  if (workspace_bytes < mica_cand_picks_workspace_bytes(cap))
+    return set_error(MICA_ERR_WORKSPACE, "picks workspace too small");
+  char* ws = (char*)workspace;
+  uint32_t* counts = (uint32_t*)ws;
+  uint32_t* fill = (uint32_t*)(ws + align256(kRankBuckets * sizeof(uint32_t)));
+  long long* first = (long long*)(ws + 2 * align256(kRankBuckets * sizeof(uint32_t)));
+  char* q = (char*)first + align256(kRankBuckets * sizeof(long long));
+  long long* picked_lin = (long long*)q; q += align256((size_t)cap * sizeof(long long));
+  float* picked_p = (float*)q; q += align256((size_t)cap * sizeof(float));
+  long long* bucket_lin = (long long*)q; q += align256((size_t)cap * sizeof(long long));
+  float* bucket_p = (float*)q;
+  nms_collect_kernel<<<grid_for(n, 256), 256, 0, st>>>(work, (const long long*)lin, valid, n, cap, picked_lin,
+                                                       picked_p, (unsigned long long*)n_picks_dev);
   MICA_LAUNCH_CHECK("nms_collect_kernel");
   int64_t m = 0;
   MICA_CUDA(cudaMemcpyAsync(&m, n_picks_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
   MICA_CUDA(cudaStreamSynchronize(st));
   if (m > cap) return set_error(MICA_ERR_WORKSPACE, "%lld picks exceed the capacity %lld", (long long)m, (long long)cap);
   if (m > 0) {
-    nms_rank_kernel<<<grid_for(m, 256), 256, 0, st>>>((const long long*)scratch_lin, scratch_p, m, Y, Z,
+    MICA_CUDA(cudaMemsetAsync(counts, 0, 2 * align256(kRankBuckets * sizeof(uint32_t)), st));  // counts + fill
+    nms_bucket_count_kernel<<<grid_for(m, 256), 256, 0, st>>>(picked_p, m, counts);
+    MICA_LAUNCH_CHECK("nms_bucket_count_kernel");
+    scan_u32_kernel<<<1, 1024, 0, st>>>(counts, kRankBuckets, first, nullptr);
+    MICA_LAUNCH_CHECK("scan_u32_kernel");
+    nms_bucket_scatter_kernel<<<grid_for(m, 256), 256, 0, st>>>(picked_lin, picked_p, m, first, fill, bucket_lin,
+                                                                bucket_p);
+    MICA_LAUNCH_CHECK("nms_bucket_scatter_kernel");
+    nms_rank_kernel<<<grid_for(m, 256), 256, 0, st>>>(bucket_lin, bucket_p, m, first, counts, Y, Z,
                                                       (long long*)sorted_lin, sorted_xyz);
     MICA_LAUNCH_CHECK("nms_rank_kernel");
   }

@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 from mica_b200 import mrc, pdb, synthetic
 from mica_b200.pipeline import MapHeader, zoom_factors
@@ -80,3 +81,69 @@ def test_header_transpose_and_zoom_bookkeeping():
         assert list(perm) == list(operm) and off == ooff
     v = (np.float32(1.06), np.float32(1.13), np.float32(0.97))
     assert [float(a) for a in zoom_factors(v)] == [float(a) for a in orc.zoom_factors(v)]
+
+
+# ---------------------------------------------------------------- host logic of the SURVEY 8(f) mirrors (no GPU)
+def test_valid_labels_follow_the_reference_cluster_filter():
+    """candidates.valid_labels (host part of utils/modeler.py:781-797) against the oracle's restatement."""
+    from mica_b200 import candidates as cd
+    from oracle import candidates_oracle as co
+    rng = np.random.default_rng(4)
+    bb = rng.random((12, 12, 12), dtype=np.float32)
+    pts = np.array(np.where(rng.random((12, 12, 12)) < 0.3)).T
+    labels = rng.integers(-1, 6, len(pts))
+    labels[:40] = 5                                                   # one dominant cluster
+    bb[tuple(pts[labels == 2].T)] *= 0.05                             # one weak cluster (dropped by the sum test)
+    val, sums, avgs = co.valid_clusters(pts, labels, bb)
+    at = bb[pts[:, 0], pts[:, 1], pts[:, 2]].astype(np.float64)
+    s64 = np.array([at[labels == k].sum() for k in range(6)])
+    cnt = np.array([(labels == k).sum() for k in range(6)])
+    ok, s32, a32 = cd.valid_labels(s64, cnt)
+    assert np.allclose(s32, sums, rtol=1e-6) and np.allclose(a32, avgs, rtol=1e-6)
+    assert np.array_equal(ok[labels[labels >= 0]], val[labels >= 0]) and not val[labels < 0].any()
+    assert not ok.all() and ok.any()
+    with pytest.raises(ValueError):                                   # np.max of an empty list in the reference
+        cd.valid_labels(np.zeros(0), np.zeros(0, np.int64))
+
+
+def test_pdb_records_and_central_atom_selection(tmp_path):
+    from mica_b200 import dock_masks as dm, pdb, synthetic
+    from oracle import masks_oracle as mo
+    st = synthetic.synthetic_structure(40, (30, 30, 30), seed=3, hetero_every=5, unknown_every=7)
+    p = str(tmp_path / 's.pdb')
+    synthetic.write_pdb(p, st)
+    rec = pdb.read_pdb_records(p)
+    assert np.array_equal(rec['coords'], st['coords'])                # ATOM and HETATM records, file order
+    assert rec['atom_names'] == list(st['atom_names']) and rec['res_names'] == list(st['res_names'])
+    assert rec['res_index'][0] == 0 and rec['res_index'][-1] == 39 and np.all(np.diff(rec['res_index']) >= 0)
+    atoms_only, _, _, n_res = pdb.read_pdb_atoms(p)
+    assert len(atoms_only) < len(rec['coords'])                       # the AF3 encoder skips hetero residues
+    for method in ('median', 'mean'):
+        assert np.array_equal(dm.select_central_atoms(rec['coords'], 40, method),
+                              mo.select_central_atoms(rec['coords'], 40, method))
+    with pytest.raises(ValueError):
+        dm.select_central_atoms(rec['coords'], 40, 'mode')
+
+
+def test_next_row_mirrors_fail_loudly_without_a_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    from mica_b200 import _lib, candidates as cd, dock_masks as dm, label_masks as lm, mrc
+    vols = {k: np.zeros((4, 4, 4), np.float32) for k in ('carbon_alpha_probability', 'backbone_probability',
+                                                        'amino_acid_prediction')}
+    vols['amino_acid_probability'] = np.zeros((20, 4, 4, 4), np.float32)
+    with pytest.raises(_lib.MicaError):
+        cd.find_candidates(vols)
+    with pytest.raises(_lib.MicaError):
+        cd.neighbor_graph(np.zeros((3, 3)), np.zeros((4, 4, 4), np.float32))
+    with pytest.raises(_lib.MicaError):
+        lm.class_mask(torch.zeros((1, 3)), torch.zeros(1, dtype=torch.uint8), (0, 0, 0), (4, 4, 4))
+    with pytest.raises(_lib.MicaError):
+        dm.contour_threshold(torch.zeros(8), 0.1)
+    p = str(tmp_path / 'm.mrc')
+    mrc.write_mrc(p, mrc.MrcMap(data=np.zeros((4, 4, 4), np.float32)))
+    with pytest.raises(_lib.MicaError):
+        lm.BackboneMask(p)
+    with pytest.raises(_lib.MicaError):
+        dm.DockingMapMasks()
