@@ -1,4 +1,5 @@
-"""BASELINE.json configs 2-5 at their full sizes.  Where the CPU oracle finishes in seconds it is
+"""BASELINE.json configs 1-5 at their full sizes (config 1 = configs[0], the reference's own CPU-runnable case,
+is small enough for the oracle to run the whole path).  Where the CPU oracle finishes in seconds it is
 used directly (order statistics of 110.6 M voxels, atom indices of 20 k residues); elsewhere the
 check is a size-independent property of the path: extract -> stitch is the identity, the sparse
 AF3 cube fill equals the dense volume's windows, resampling is linear and reproduces constants,
@@ -24,6 +25,59 @@ def _smooth_random(shape, device, seed):
     blobs = torch.rand(shape, generator=g, device=device)
     v += torch.where(blobs > 0.97, blobs * 4 - 3.5, torch.zeros((), device=device))
     return torch.nn.functional.avg_pool3d(v[None, None], 3, 1, 1)[0, 0].contiguous()
+
+
+# ----------------------------------------------------------------------- config 1: 200^3 @ 1.06 A -> 212^3
+def test_config1_200_map_whole_path_against_the_oracle(cuda):
+    """BASELINE configs[0]: synthetic 200^3 map, 1.06 A voxel, 3.7 A resolution, reference defaults
+    (grid_size 48, padding 8 -> 125 cubes): every stage of the GPU path against the oracle's."""
+    src = synthetic.synthetic_map((200, 200, 200), voxel=1.06, resolution=3.7, seed=2022)
+    voxel = (np.float32(1.06),) * 3
+    hdr = MapHeader(voxel_size=voxel)
+    st = synthetic.synthetic_structure(1700, (212, 212, 212), seed=2022)
+    bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
+    atoms = tuple(torch.from_numpy(a).to(cuda) for a in (st['coords'], bb_ch, aa_ch))
+    ring = synthetic.synthetic_logits(16, 64, seed=2022)
+    d_ring = [torch.from_numpy(a).to(cuda) for a in ring]
+    seen = {}
+
+    def model_fn(x, af):
+        seen[len(seen)] = (x[:2].cpu().numpy(), af[:2].cpu().numpy())       # first two cubes of every batch
+        return tuple(t[:x.shape[0]] for t in d_ring)
+
+    pipe = MapPipeline(cuda, 48, 8, batch_cubes=16)
+    vols = pipe.run(torch.from_numpy(src).to(cuda), hdr, atoms, model_fn)
+    assert tuple(pipe.normalized.shape) == (212, 212, 212) and len(pipe.ijk_host) == 125
+    # R1-R3
+    o_norm, med, p = orc.normalize(orc.resample(src, voxel))
+    assert np.abs(pipe.normalized.cpu().numpy() - o_norm).max() <= 1e-5
+    # R4 (bit-exact) and R5/R6 on the cubes the model saw
+    o_af3, ok = orc.af3_encode(st['coords'], bb_ch, aa_ch, (0.0, 0.0, 0.0), o_norm.shape)
+    assert ok
+    o_cubes, meta, shp, _ = orc.extract_cubes(o_norm)
+    for b, (x, af) in seen.items():
+        for r in range(len(x)):
+            c = 16 * b + r
+            assert np.abs(x[r, 0] - o_cubes[c]).max() <= 1e-5
+            i, j, k = (int(v) for v in meta[c][:3])
+            want = np.zeros((24, 64, 64, 64), np.float32)
+            t = np.transpose(o_af3, (0, 3, 2, 1))
+            xs, ys, zs = (slice(max(0, a - 8), min(212, a + 56)) for a in (i, j, k))
+            want[:, xs.start - i + 8:xs.stop - i + 8, ys.start - j + 8:ys.stop - j + 8,
+                 zs.start - k + 8:zs.stop - k + 8] = t[:, xs, ys, zs]
+            assert np.array_equal(af[r], want), c
+    # R7/R8: reference post-processing + stitching of the same logits, 16 cubes at a time
+    want = {'backbone_probability': np.zeros(shp, np.float32), 'carbon_alpha_probability': np.zeros(shp, np.float32),
+            'amino_acid_prediction': np.zeros(shp, np.float32), 'amino_acid_probability': np.zeros((20,) + tuple(shp), np.float32)}
+    for c0 in range(0, 125, 16):
+        n = min(16, 125 - c0)
+        bb, ca, aa_prob, aa_pred = orc.postprocess(ring[0][:n], ring[1][:n], ring[2][:n])
+        for name, pred in (('backbone_probability', bb), ('carbon_alpha_probability', ca),
+                           ('amino_acid_prediction', aa_pred), ('amino_acid_probability', aa_prob)):
+            orc.stitch(pred, meta[c0:c0 + n], shp, name, 8, volume=want[name])
+    for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+        assert np.abs(vols.as_dict()[k].cpu().numpy() - want[k]).max() <= 1e-5, k
+    assert (vols.amino_acid_prediction.cpu().numpy() == want['amino_acid_prediction']).mean() > 0.9999
 
 
 # ----------------------------------------------------------------------- config 2: 400^3 -> 480^3
