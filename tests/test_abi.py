@@ -70,3 +70,50 @@ def test_product_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle', text, flags=re.M), f
                 assert 'scipy.ndimage import zoom' not in text, f
+
+
+def _prototypes():
+    src = open(os.path.join(ROOT, 'include', 'mica_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\b(mica_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', src):
+        args = m.group(2).strip()
+        protos[m.group(1)] = [] if args in ('', 'void') else [a.strip() for a in args.split(',')]
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Argument count and the pointer / integer / float class of every parameter: a drifted binding would
+    otherwise only show up as garbage on the GPU box."""
+    from mica_b200 import _lib
+    protos = _prototypes()
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, params in protos.items():
+        argtypes = _lib.SIGNATURES[name][1]
+        assert len(params) == len(argtypes), f'{name}: header has {len(params)} parameters, ctypes {len(argtypes)}'
+        for decl, ct in zip(params, argtypes):
+            is_ptr = '*' in decl or '[' in decl or 'mica_stream_t' in decl
+            ct_ptr = ct is ctypes.c_void_p or ct is ctypes.c_char_p or hasattr(ct, 'contents') or \
+                (isinstance(ct, type) and issubclass(ct, ctypes._Pointer))
+            assert is_ptr == ct_ptr, f'{name}: `{decl}` bound as {ct}'
+            if not is_ptr:
+                base = decl.replace('const', '').split()[0]
+                want = {'int': ctypes.c_int, 'int64_t': ctypes.c_int64, 'float': ctypes.c_float,
+                        'double': ctypes.c_double, 'size_t': ctypes.c_size_t}[base]
+                assert ct is want, f'{name}: `{decl}` bound as {ct}'
+
+
+def test_new_entry_points_reject_bad_arguments_before_touching_the_device():
+    from mica_b200 import _lib
+    lib = _lib.lib
+    assert lib.mica_cand_threshold_count(None, 64, 0.3, None, 0, None, None) == -1
+    assert b'null' in lib.mica_last_error()
+    assert lib.mica_dbscan_lattice(None, 5, 4, 4, 4, 100, 10, None, 0, None, None, None) == -1
+    assert lib.mica_cand_neighbor_graph(None, 70000, None, 4, 4, 4, None, None, None) == -1
+    assert lib.mica_label_class_mask(None, None, 1 << 30, 0, 0, 0, 3, 3, 3, 4, 4, 4, None, None, None) == -1
+    assert lib.mica_label_aa_mask(None, None, 0, 0, 0, 0, 3, 3, 3, 0, 4, 4, None, 0, None, None, None) == -1
+    assert lib.mica_zero_around_atoms(None, 1, None, None, 2.0, 4, 4, 4, None, None, None) == -1
+    assert lib.mica_contour_threshold_f32(None, None, 8, 0.1, None) == -1
+    assert lib.mica_contour_threshold_f32(None, None, 0, 0.1, None) == 0          # nothing to do
+    assert lib.mica_cand_threshold_workspace_bytes(480 ** 3) > 27000 * 12
+    assert lib.mica_label_aa_mask_workspace_bytes(4, 5, 6) == 3 * 4 * 120
