@@ -136,7 +136,30 @@ int mica_peer_open(const void* ipc_handle, void** dev_ptr);
 int mica_peer_close(void* dev_ptr);
 int mica_peer_free(void* dev_ptr);
 int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, int rank, int world, int parity, int epoch,
+                            int step /* host step 0..MICA_SELECT_PASSES-1; a step that is not due on the device
+                                        (the fallback after an accepted guided pass) skips the handshake */,
                             mica_stream_t stream);
+
+/* ------------------------------------------- multi-GPU: z-halo exchange of the source map over peer memory
+ * No reference counterpart.  A rank of the z-slab partition (mica_b200/slab.py) needs a few source planes
+ * of each neighbour (interpolation taps + prefilter horizon).  Every rank owns one exported buffer
+ * (mica_ipc_alloc of mica_halo_buffer_bytes(slot_elems); handles exchanged once; peers opened with
+ * mica_peer_open) and a table of `world` device pointers as above.  Per map, on the caller's stream:
+ *   mica_halo_publish  copies `n_lo` / `n_hi` elements starting at element offsets `off_lo` / `off_hi` of the
+ *                      rank's own block into its buffer (slot `parity`), then raises a flag in each neighbour's
+ *                      buffer (st.release.sys) -- it never waits;
+ *   mica_halo_pull     waits (ld.acquire.sys, bounded: *status becomes 1 on timeout) for the neighbours' flags
+ *                      of `epoch` and copies the `n_lo` elements the LOWER neighbour published for this rank
+ *                      to dst_lo and the `n_hi` elements of the UPPER neighbour to dst_hi, over NVLink.
+ * `epoch` increases by one per exchange, `parity` = epoch & 1 (slot reuse is safe because the order-statistics
+ * exchange of the map in between synchronises all ranks). */
+size_t mica_halo_buffer_bytes(int64_t slot_elems);
+int mica_ipc_alloc(size_t bytes, void** dev_ptr, void* ipc_handle_out /* 64 bytes, nullable */);
+int mica_halo_publish(const float* own, int64_t off_lo, int64_t n_lo, int64_t off_hi, int64_t n_hi,
+                      void* const* peer_bufs, int rank, int world, int parity, int epoch, int64_t slot_elems,
+                      mica_stream_t stream);
+int mica_halo_pull(float* dst_lo, int64_t n_lo, float* dst_hi, int64_t n_hi, void* const* peer_bufs, int rank,
+                   int world, int parity, int epoch, int64_t slot_elems, int* status, mica_stream_t stream);
 
 /* test hooks for the normaliser: (1) evaluate the NumPy expression operation by operation for
  * every voxel instead of the short equivalent path (returns the previous setting); (2) put
@@ -232,6 +255,17 @@ int mica_postproc_stitch(const float* bb, const float* ca, const float* aa,
 int mica_stitch_cubes(const float* cubes, int n_ch, const int32_t* ijk, int n_cubes,
                       int X, int Y, int Z, const int org[3], const int ext[3],
                       int grid_size, int padding, float* vol, mica_stream_t stream);
+
+/* Multi-GPU form of mica_postproc_stitch (config 5: the cubes of ONE map dealt out evenly over the ranks,
+ * no reference counterpart): the output is partitioned along cube axis 0, rank r owning planes
+ * [x_bounds[r], x_bounds[r+1]) as 23 float32 channels of [x_bounds[r+1]-x_bounds[r], Y, Z] at owner_base[r]
+ * ([backbone | carbon_alpha | amino_acid_prediction | amino_acid_probability x 20]); owner_base is a DEVICE
+ * array of `world` pointers into peer-mapped memory (mica_ipc_alloc / mica_peer_open).  Every core plane is
+ * stored straight into its owner's block over NVLink -- softmax/argmax + stitch fused with the exchange.
+ * The caller synchronises all ranks (stream sync + barrier) before an owner reads its block. */
+int mica_postproc_stitch_peer(const float* bb, const float* ca, const float* aa, const int32_t* ijk, int n_cubes,
+                              int X, int Y, int Z, int grid_size, int padding, void* const* owner_base,
+                              const int* x_bounds, int world, mica_stream_t stream);
 
 /* ===================================================================================
  * SURVEY.md section 8(f) "next" rows, built to the same bar as R1-R8.

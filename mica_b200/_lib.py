@@ -60,7 +60,11 @@ SIGNATURES = {
     'mica_peer_open': (_i, [_p, C.POINTER(_p)]),
     'mica_peer_close': (_i, [_p]),
     'mica_peer_free': (_i, [_p]),
-    'mica_select_peer_reduce': (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    'mica_select_peer_reduce': (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    'mica_halo_buffer_bytes': (_sz, [_i64]),
+    'mica_ipc_alloc': (_i, [_sz, C.POINTER(_p), _p]),
+    'mica_halo_publish': (_i, [_p, _i64, _i64, _i64, _i64, _p, _i, _i, _i, _i, _i64, _p]),
+    'mica_halo_pull': (_i, [_p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i64, _p, _p]),
     'mica_af3_encode': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     'mica_af3_bins_workspace_bytes': (_sz, [_i64, _i, _i, _i, C.POINTER(_i), _i, _i]),
     'mica_af3_bin_atoms': (_i, [_p, _p, _p, _i64, _f, _f, _f, _i, _i, _i, _i, _i, _i, C.POINTER(_i), _i, _i,
@@ -72,6 +76,7 @@ SIGNATURES = {
     'mica_postproc_stitch': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i,
                                   _p, _p, _p, _p, _p]),
     'mica_stitch_cubes': (_i, [_p, _i, _p, _i, _i, _i, _i, C.POINTER(_i), C.POINTER(_i), _i, _i, _p, _p]),
+    'mica_postproc_stitch_peer': (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, C.POINTER(_i), _i, _p]),
     # candidates
     'mica_cand_threshold_workspace_bytes': (_sz, [_i64]),
     'mica_cand_threshold_count': (_i, [_p, _i64, _f, _p, _sz, _p, _p]),

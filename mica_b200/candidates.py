@@ -23,7 +23,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import lib, check
-from .ops import _dev, _stream
+from .ops import _dev, _stream, device_guard
 
 VOLUME_KEYS = ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction',
                'amino_acid_probability')
@@ -48,6 +48,7 @@ def _as_device(v, device):
     return torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).to(device)
 
 
+@device_guard
 def threshold_points(vol: torch.Tensor, thr: float):
     """``np.where(vol > thr)`` (utils/modeler.py:767) -> (lin int64 [n], xyz int32 [n,3]) on the device, in
     NumPy's order.  ``thr`` is compared in float32 like NumPy 2 compares a python float with a float32 array."""
@@ -69,6 +70,7 @@ def threshold_points(vol: torch.Tensor, thr: float):
     return lin, xyz
 
 
+@device_guard
 def gather(vol: torch.Tensor, lin: torch.Tensor) -> torch.Tensor:
     out = torch.empty(lin.shape[0], dtype=torch.float32, device=vol.device)
     if lin.shape[0]:
@@ -77,6 +79,7 @@ def gather(vol: torch.Tensor, lin: torch.Tensor) -> torch.Tensor:
     return out
 
 
+@device_guard
 def dbscan_lattice(lin: torch.Tensor, shape_xyz, eps, min_points):
     """Open3D ``cluster_dbscan(eps, min_points)`` (utils/modeler.py:770) for distinct lattice points given as
     ascending linear indices.  Returns (labels int32 [n] on the device, number of clusters)."""
@@ -95,6 +98,7 @@ def dbscan_lattice(lin: torch.Tensor, shape_xyz, eps, min_points):
     return labels, _scalar_i64(ncl)
 
 
+@device_guard
 def cluster_scores(bb_at: torch.Tensor, labels: torch.Tensor, n_labels: int):
     """Per-label (sum float64, count int64) of the backbone probability at the points -> host arrays."""
     dev = bb_at.device
@@ -200,6 +204,7 @@ def find_candidates(volumes, CA_score_thrh=0.3, cluster_eps=10, cluster_min_poin
     return res
 
 
+@device_guard
 def clustered_volume(ca: torch.Tensor, lin: torch.Tensor, valid: torch.Tensor) -> torch.Tensor:
     """``NNPred.CAProb_clusted`` (utils/modeler.py:800-802) on the device."""
     out = torch.empty_like(ca)

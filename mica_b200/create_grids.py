@@ -2,8 +2,9 @@
 
 Same method names, arguments and result dictionaries (utils/create_grids.py:205-397).
 By default no per-cube ``.npz`` file is written: the cube index (origins, window,
-axis permutation) and the resident volume are registered under ``output_dir`` for
-CryoEMPredictor, and the cubes are cut on the GPU straight into the model batch.
+axis permutation) and the resident volume -- or, for the AF3 channels, just the atoms --
+are registered under ``output_dir`` for CryoEMPredictor, which cuts the cubes on the GPU
+straight into the model batch on the pipeline DataPreprocessor started.
 ``materialize=True`` also writes the reference's files (same names and keys)."""
 from __future__ import annotations
 
@@ -47,7 +48,9 @@ class GridCreator:
     def _load(self, path):
         entry = session.get(path)
         if entry is not None:
+            self._pipe = entry.get('pipe')
             return entry['volume'], entry['header']
+        self._pipe = None
         m = mrc.read_mrc(path)
         hdr = MapHeader(voxel_size=m.voxel_size, origin=m.origin, mapc=m.mapc, mapr=m.mapr, maps=m.maps,
                         nxstart=m.nxstart, nystart=m.nystart, nzstart=m.nzstart)
@@ -82,7 +85,8 @@ class GridCreator:
             vol, header = self._load(mrc_file)
             perm, offset, cube_shape, ijk = self._index(tuple(vol.shape), header, grid_size)
             session.put(output_dir, kind='cubes', volume=vol, header=header, perm=perm, offset=offset,
-                        cube_shape=cube_shape, ijk=ijk, grid_size=grid_size, padding=padding, prefix=file_prefix)
+                        cube_shape=cube_shape, ijk=ijk, grid_size=grid_size, padding=padding, prefix=file_prefix,
+                        pipe=self._pipe, source=mrc_file)
             if self.materialize:
                 self._write_npz(vol, header, perm, cube_shape, ijk, output_dir, grid_size, padding, file_prefix)
             return len(ijk), offset
@@ -113,8 +117,10 @@ class GridCreator:
             return {'success': False, 'error': error_msg}
         errors, ok_channels = [], 0
         try:
+            atoms, pipe = None, None
             if entry is not None:
                 vol, header, names = entry['volume'], entry['header'], list(pdb.CHANNEL_NAMES)
+                atoms, pipe = entry.get('atoms'), entry.get('pipe')
             else:
                 files = glob.glob(os.path.join(AF3_encodings_path, '*_encoding.mrc'))
                 if not files:
@@ -133,11 +139,13 @@ class GridCreator:
                         np.array(m.data, dtype=np.float32)).to(self.device)
             perm, offset, cube_shape, ijk = self._index(tuple(vol.shape[1:]), header, grid_size)
             session.put(output_dir, kind='af3_cubes', volume=vol, header=header, perm=perm, offset=offset,
-                        cube_shape=cube_shape, ijk=ijk, grid_size=grid_size, padding=padding, channels=names)
+                        cube_shape=cube_shape, ijk=ijk, grid_size=grid_size, padding=padding, channels=names,
+                        atoms=atoms, pipe=pipe, source=AF3_encodings_path)
             if self.materialize:
+                dense = vol.get() if hasattr(vol, 'get') else vol      # LazyAf3Volume: rasterise now
                 for name in names:
                     c = pdb.CHANNEL_NAMES.index(name)
-                    self._write_npz(vol[c], header, perm, cube_shape, ijk,
+                    self._write_npz(dense[c], header, perm, cube_shape, ijk,
                                     os.path.join(output_dir, f'{name}_grids'), grid_size, padding, f'{name}_grid')
             ok_channels = len(names)
         except Exception as e:

@@ -76,4 +76,15 @@ __device__ __forceinline__ void st_stream4(float4* p, float4 v) {
                : "memory");
 }
 
+// system-scope release / acquire on a flag word in (possibly peer) global memory: the PTX-model form of
+// "data, fence, flag" between GPUs
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 }  // namespace mica

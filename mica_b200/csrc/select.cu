@@ -596,23 +596,25 @@ struct PeerBuffer {
 
 __global__ void __launch_bounds__(1024)
 select_peer_reduce_kernel(SelectState* __restrict__ s, PeerBuffer* const* __restrict__ peers, int rank, int world,
-                          int parity, int epoch, long long timeout_cycles) {
+                          int parity, int epoch, int step, long long timeout_cycles) {
   __shared__ int ok;
+  // a host step whose data pass did not run has nothing to exchange: the full-histogram fallback (step 2)
+  // after an accepted guided pass, or anything once the status is final.  The state that decides this is
+  // derived from the reduced histograms, so it is the same on every rank and all ranks skip together.
+  if (s->status != MICA_NORM_PENDING || (step == 2 && s->phase0 != 2)) return;
   PeerBuffer* mine = peers[rank];
   long long* local = &s->hist[0][0];
   for (int i = threadIdx.x; i < kPeerSlotWords; i += blockDim.x) mine->slot[parity][i] = local[i];
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x < world) {   // raise my flag in every peer's buffer (and my own)
-    volatile int* f = &peers[threadIdx.x]->flag[rank];
-    *f = epoch;
-  }
+  if (threadIdx.x < world)     // raise my flag in every peer's buffer (and my own)
+    st_release_sys(&peers[threadIdx.x]->flag[rank], epoch);
   if (threadIdx.x == 0) ok = 1;
   __syncthreads();
   if (threadIdx.x < world) {   // wait for peer threadIdx.x
-    volatile int* f = &mine->flag[threadIdx.x];
+    const int* f = &mine->flag[threadIdx.x];
     const long long t0 = clock64();
-    while (*f - epoch < 0) {
+    while (ld_acquire_sys(f) - epoch < 0) {
       if (clock64() - t0 > timeout_cycles) {
         ok = 0;
         break;
@@ -787,11 +789,8 @@ extern "C" int mica_select_hist(const float* x, int64_t n_local, void* workspace
     int64_t grid0 = ceil_div64(n_local, kHist0Warps * kHist0MaxPerWarp);
     if (grid0 < 2 * kNumSMs) grid0 = want < 2 * kNumSMs ? want : 2 * kNumSMs;
     const size_t smem0 = (size_t)kHist0Warps * kBins * sizeof(unsigned short);
-    static bool attr_set = false;
-    if (!attr_set) {
-      MICA_CUDA(cudaFuncSetAttribute(select_hist0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
-      attr_set = true;
-    }
+    // per device/context attribute: set it on every call (a process-wide flag would leave the other GPUs unset)
+    MICA_CUDA(cudaFuncSetAttribute(select_hist0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
     select_hist0_kernel<<<(unsigned)grid0, 512, smem0, st>>>(x, n_local, s);
     MICA_LAUNCH_CHECK("select_hist0_kernel");
   } else {
@@ -866,13 +865,14 @@ extern "C" int mica_peer_free(void* dev_ptr) {
 }
 
 extern "C" int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, int rank, int world, int parity,
-                                       int epoch, mica_stream_t stream) {
+                                       int epoch, int step, mica_stream_t stream) {
   MICA_REQUIRE(workspace && peer_bufs, "null pointer");
   MICA_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world");
   MICA_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
   const long long timeout_cycles = 4000000000LL;   // ~2 s at 1.9 GHz
   select_peer_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
-      state_of(workspace), reinterpret_cast<PeerBuffer* const*>(peer_bufs), rank, world, parity, epoch, timeout_cycles);
+      state_of(workspace), reinterpret_cast<PeerBuffer* const*>(peer_bufs), rank, world, parity, epoch, step,
+      timeout_cycles);
   MICA_LAUNCH_CHECK("select_peer_reduce_kernel");
   return MICA_OK;
 }

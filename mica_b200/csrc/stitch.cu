@@ -15,6 +15,17 @@
 
 namespace mica {
 
+constexpr int kStitchMaxWorld = 64;
+
+// multi-GPU ownership of the output along cube axis 0 (x): rank r owns planes [bounds[r], bounds[r+1]) and
+// holds them as 23 channels of [bounds[r+1]-bounds[r], Y, Z] floats at base[r] (peer memory, mapped here):
+// [backbone | carbon_alpha | amino_acid_prediction | amino_acid_probability x 20]
+struct StitchOwners {
+  float* const* base;
+  int world;
+  int bounds[kStitchMaxWorld + 1];
+};
+
 struct StitchParams {
   const float* bb;
   const float* ca;
@@ -48,8 +59,12 @@ __device__ __forceinline__ float softmax3_last(float l0, float l1, float l2) {
 // is thousands of small CTAs and the last wave over the 148 SMs is short.  The cube is the FASTEST
 // grid index: cubes that follow each other in the batch are neighbours along the volume's fastest
 // axis (k), so CTAs resident together write adjacent 128-byte runs of the same output rows
+// PEER: the destination of a core plane is the volume block of the rank that owns its x plane -- the
+// local one or a peer's, written over NVLink (coalesced 128-byte runs, fire and forget).  The owner is
+// uniform per CTA (a CTA handles one core plane), so the lookup costs nothing per voxel.
+template <bool PEER>
 __global__ void __launch_bounds__(256)
-postproc_stitch_kernel(StitchParams P) {
+postproc_stitch_kernel(StitchParams P, StitchOwners O) {
   const int S = P.S, W = P.W;
   const int chunks = (S * S + 255) >> 8;
   const int a = blockIdx.y / chunks, b = blockIdx.x;
@@ -60,7 +75,19 @@ postproc_stitch_kernel(StitchParams P) {
   const float* bb = P.bb + (int64_t)b * 4 * W3;
   const float* ca = P.ca + (int64_t)b * 4 * W3;
   const float* aa = P.aa + (int64_t)b * 21 * W3;
-  const int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
+  int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
+  int x_org = P.org[0];
+  if (PEER) {
+    int r = 0;
+    while (r + 1 < O.world && gx >= O.bounds[r + 1]) ++r;
+    x_org = O.bounds[r];
+    vol_n = (int64_t)(O.bounds[r + 1] - O.bounds[r]) * P.ext[1] * P.ext[2];
+    float* base = O.base[r];
+    P.bb_vol = base;
+    P.ca_vol = base + vol_n;
+    P.aa_pred_vol = base + 2 * vol_n;
+    P.aa_prob_vol = base + 3 * vol_n;
+  }
   {
     const int e = (blockIdx.y - a * chunks) * 256 + threadIdx.x;
     if (e >= S * S) return;
@@ -70,7 +97,7 @@ postproc_stitch_kernel(StitchParams P) {
     const int ly = gy - P.org[1], lz = gz - P.org[2];
     if ((unsigned)ly >= (unsigned)P.ext[1] || (unsigned)lz >= (unsigned)P.ext[2]) return;
     const int64_t src = ((int64_t)(a + P.pad) * W + (bj + P.pad)) * W + (c + P.pad);
-    const int64_t dst = ((int64_t)(gx - P.org[0]) * P.ext[1] + ly) * P.ext[2] + lz;
+    const int64_t dst = ((int64_t)(gx - x_org) * P.ext[1] + ly) * P.ext[2] + lz;
     // issue every load before the math: 26 independent requests in flight per thread
     const float b0 = ld_stream_half_line(bb + src), b2 = ld_stream_half_line(bb + 2 * W3 + src), b3 = ld_stream_half_line(bb + 3 * W3 + src);
     const float c0 = ld_stream_half_line(ca + src), c2 = ld_stream_half_line(ca + 2 * W3 + src), c3 = ld_stream_half_line(ca + 3 * W3 + src);
@@ -176,8 +203,51 @@ extern "C" int mica_postproc_stitch(const float* bb, const float* ca, const floa
     P.aa = aa + (int64_t)b0 * 21 * W3;
     P.ijk = ijk + 3 * (int64_t)b0;
     const int chunks = (grid_size * grid_size + 255) / 256;
-    postproc_stitch_kernel<<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P);
+    postproc_stitch_kernel<false><<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P, StitchOwners());
     MICA_LAUNCH_CHECK("postproc_stitch_kernel");
+  }
+  return MICA_OK;
+}
+
+extern "C" int mica_postproc_stitch_peer(const float* bb, const float* ca, const float* aa, const int32_t* ijk,
+                                         int n_cubes, int X, int Y, int Z, int grid_size, int padding,
+                                         void* const* owner_base, const int* x_bounds, int world,
+                                         mica_stream_t stream) {
+  MICA_REQUIRE(owner_base && x_bounds, "null owner table");
+  MICA_REQUIRE(world >= 1 && world <= kStitchMaxWorld, "bad world size %d", world);
+  MICA_REQUIRE(n_cubes == 0 || (bb && ca && aa && ijk), "null input");
+  MICA_REQUIRE(grid_size > 0 && padding >= 0 && X > 0 && Y > 0 && Z > 0, "bad geometry");
+  MICA_REQUIRE(x_bounds[0] == 0 && x_bounds[world] == X, "x_bounds must run from 0 to X");
+  for (int r = 0; r < world; ++r) MICA_REQUIRE(x_bounds[r] <= x_bounds[r + 1], "x_bounds must not decrease");
+  if (n_cubes <= 0) return MICA_OK;
+  StitchParams P;
+  P.X = X;
+  P.Y = Y;
+  P.Z = Z;
+  P.org[0] = P.org[1] = P.org[2] = 0;
+  P.ext[0] = X;
+  P.ext[1] = Y;
+  P.ext[2] = Z;
+  P.S = grid_size;
+  P.pad = padding;
+  P.W = grid_size + 2 * padding;
+  P.bb_vol = P.ca_vol = P.aa_prob_vol = P.aa_pred_vol = nullptr;
+  StitchOwners O;
+  O.base = reinterpret_cast<float* const*>(owner_base);
+  O.world = world;
+  for (int r = 0; r <= world; ++r) O.bounds[r] = x_bounds[r];
+  for (int r = world + 1; r <= kStitchMaxWorld; ++r) O.bounds[r] = X;
+  const int64_t W3 = (int64_t)P.W * P.W * P.W;
+  const int kMaxY = 32768;
+  for (int b0 = 0; b0 < n_cubes; b0 += kMaxY) {
+    const int nb = (n_cubes - b0 < kMaxY) ? n_cubes - b0 : kMaxY;
+    P.bb = bb + (int64_t)b0 * 4 * W3;
+    P.ca = ca + (int64_t)b0 * 4 * W3;
+    P.aa = aa + (int64_t)b0 * 21 * W3;
+    P.ijk = ijk + 3 * (int64_t)b0;
+    const int chunks = (grid_size * grid_size + 255) / 256;
+    postproc_stitch_kernel<true><<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P, O);
+    MICA_LAUNCH_CHECK("postproc_stitch_kernel<peer>");
   }
   return MICA_OK;
 }

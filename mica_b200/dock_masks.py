@@ -21,11 +21,12 @@ import torch
 
 from . import mrc, ops, pdb
 from ._lib import lib, check
-from .ops import _dev, _stream
+from .ops import _dev, _stream, device_guard
 
 _F3 = C.c_float * 3
 
 
+@device_guard
 def contour_threshold(data: torch.Tensor, contour_level: float, out: torch.Tensor | None = None) -> torch.Tensor:
     """``np.where(data < contour_level, 0, data)`` (utils/dock_in_map.py:269); float32 comparison."""
     p = _dev(data, torch.float32, 'data')
@@ -36,6 +37,7 @@ def contour_threshold(data: torch.Tensor, contour_level: float, out: torch.Tenso
     return out
 
 
+@device_guard
 def zero_around_atoms(map_data: torch.Tensor, coords: torch.Tensor, voxel_size_xyz, origin_xyz, radius=2.0):
     """utils/dock_in_map.py:330-352 in place on ``map_data`` (device float32 [nz,ny,nx]).  Returns the device
     status word (1 where the reference's ``mask[z, y, x] = True`` would raise IndexError)."""

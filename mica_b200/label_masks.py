@@ -21,7 +21,7 @@ import torch
 
 from . import mrc, ops, pdb
 from ._lib import lib, check
-from .ops import _stream
+from .ops import _stream, device_guard
 
 AA_MAPPING = {'ALA': 1, 'CYS': 2, 'ASP': 3, 'GLU': 4, 'PHE': 5, 'GLY': 6, 'HIS': 7, 'ILE': 8, 'LYS': 9,
               'LEU': 10, 'MET': 11, 'ASN': 12, 'PRO': 13, 'GLN': 14, 'ARG': 15, 'SER': 16, 'THR': 17,
@@ -33,6 +33,7 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None and t.numel() else None
 
 
+@device_guard
 def class_mask(coords: torch.Tensor, is_class: torch.Tensor, origin_xyz, shape_zyx, clip_hi_xyz=None):
     """create_backbone_mask.py:136-172 on the device: (mask int32 [nz,ny,nx], status int32 [1])."""
     nz, ny, nx = (int(v) for v in shape_zyx)
@@ -50,6 +51,7 @@ def class_mask(coords: torch.Tensor, is_class: torch.Tensor, origin_xyz, shape_z
     return mask, status
 
 
+@device_guard
 def aa_mask(ca_coords: torch.Tensor, labels: torch.Tensor, origin_xyz, shape_zyx, clip_hi_xyz=None):
     """create_amino_acid_mask.py:151-177 on the device: (mask int32 [nz,ny,nx], status int32 [1])."""
     nz, ny, nx = (int(v) for v in shape_zyx)

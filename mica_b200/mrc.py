@@ -24,25 +24,59 @@ class MrcMap:
     nxstart: int = 0
     nystart: int = 0
     nzstart: int = 0
+    mode: int = 2                             # MRC sample type of the file (2 = float32)
     extra: dict = field(default_factory=dict)
 
 
-def read_mrc(path) -> MrcMap:
+def _open_bytes(path):
+    """(header bytes, payload source).  gzip / bzip2 files are recognised by their magic numbers, as
+    ``mrcfile.open`` does, and decompressed into memory; plain files are memory-mapped."""
     with open(path, 'rb') as f:
-        hdr = f.read(1024)
-        if len(hdr) < 1024:
-            raise ValueError(f'{path}: truncated MRC header')
-        w = np.frombuffer(hdr, dtype='<i4', count=56)
-        fl = np.frombuffer(hdr, dtype='<f4', count=56)
-        nx, ny, nz, mode = (int(v) for v in w[0:4])
-        if mode not in _MODES or min(nx, ny, nz) <= 0:
-            raise ValueError(f'{path}: unsupported MRC (mode={mode}, shape={(nz, ny, nx)})')
-        nsymbt = int(w[23])
-        f.seek(1024 + max(nsymbt, 0))
-        dt = np.dtype(_MODES[mode]).newbyteorder('<')
-        data = np.frombuffer(f.read(dt.itemsize * nx * ny * nz), dtype=dt)
-        if data.size != nx * ny * nz:
+        magic = f.read(3)
+    if magic[:2] == b'\x1f\x8b':
+        import gzip
+        with gzip.open(path, 'rb') as f:
+            return f.read()
+    if magic == b'BZh':
+        import bz2
+        with bz2.open(path, 'rb') as f:
+            return f.read()
+    return None
+
+
+def read_mrc(path) -> MrcMap:
+    """Header + payload of an MRC2014 file.  The byte order comes from the machine stamp (0x11 0x11 =
+    big-endian, anything else is read little-endian like the files every writer of this pipeline
+    produces).  ``data`` keeps the file's sample type (``mode`` says which); for plain files it is a
+    copy-on-write memory map, so nothing is read before the caller touches it."""
+    blob = _open_bytes(path)
+    if blob is None:
+        with open(path, 'rb') as f:
+            hdr = f.read(1024)
+    else:
+        hdr = blob[:1024]
+    if len(hdr) < 1024:
+        raise ValueError(f'{path}: truncated MRC header')
+    bo = '>' if hdr[212:214] == b'\x11\x11' else '<'
+    w = np.frombuffer(hdr, dtype=bo + 'i4', count=56)
+    fl = np.frombuffer(hdr, dtype=bo + 'f4', count=56)
+    nx, ny, nz, mode = (int(v) for v in w[0:4])
+    if mode not in _MODES or min(nx, ny, nz) <= 0:
+        raise ValueError(f'{path}: unsupported MRC (mode={mode}, shape={(nz, ny, nx)})')
+    nsymbt = max(int(w[23]), 0)
+    dt = np.dtype(_MODES[mode]).newbyteorder(bo)
+    count = nx * ny * nz
+    if blob is None:
+        import os
+        if os.path.getsize(path) < 1024 + nsymbt + dt.itemsize * count:
             raise ValueError(f'{path}: truncated MRC payload')
+        data = np.memmap(path, dtype=dt, mode='c', offset=1024 + nsymbt, shape=(count,))
+    else:
+        data = np.frombuffer(blob, dtype=dt, count=-1, offset=1024 + nsymbt)[:count]
+        if data.size != count:
+            raise ValueError(f'{path}: truncated MRC payload')
+    if bo == '>':
+        data = data.astype(dt.newbyteorder('<'))
     mx, my, mz = (int(v) for v in w[7:10])
     cella = fl[10:13]
     f32 = np.float32
@@ -50,7 +84,7 @@ def read_mrc(path) -> MrcMap:
     return MrcMap(data=data.reshape(nz, ny, nx), voxel_size=vs,
                   origin=tuple(f32(v) for v in fl[49:52]),
                   mapc=int(w[16]), mapr=int(w[17]), maps=int(w[18]),
-                  nxstart=int(w[4]), nystart=int(w[5]), nzstart=int(w[6]))
+                  nxstart=int(w[4]), nystart=int(w[5]), nzstart=int(w[6]), mode=mode)
 
 
 def write_mrc(path, m: MrcMap, dtype=np.float32):

@@ -6,6 +6,7 @@ unless its tensors live on a CUDA device: there is no CPU path."""
 from __future__ import annotations
 
 import ctypes as C
+import functools
 
 import numpy as np
 import torch
@@ -17,7 +18,42 @@ STANDARD_PERM = (2, 1, 0)     # trans_order for mapc,mapr,maps = 1,2,3 (utils/cr
 
 
 def _stream():
+    """The caller's stream on the CURRENT device -- every entry point runs under ``device_guard``,
+    which makes the device of its tensors current first (the C ABI launches on the CUDA runtime's
+    current device)."""
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _cuda_device_of(a):
+    if isinstance(a, torch.Tensor):
+        return a.device if a.is_cuda else None
+    d = getattr(a, 'device', None)
+    if isinstance(d, torch.device) and d.type == 'cuda':
+        return d if d.index is not None else torch.device('cuda', torch.cuda.current_device())
+    return None
+
+
+def device_guard(fn):
+    """Run ``fn`` with the device of its CUDA arguments current: tensors, and objects that carry a
+    ``.device`` (OrderStats, Af3CubeFiller, StitchedVolumes).  All of them must live on ONE
+    device; a call whose tensors sit on cuda:1 while cuda:0 is current would otherwise launch on
+    GPU 0, on a GPU-0 stream, against GPU-1 pointers."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        dev = None
+        for a in args + tuple(kw.values()):
+            d = _cuda_device_of(a)
+            if d is None:
+                continue
+            if dev is None:
+                dev = d
+            elif d != dev:
+                raise _lib.MicaError(f'{fn.__name__}: arguments live on different devices ({dev} and {d})')
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kw)
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _dev(t: torch.Tensor, dtype, name: str):
@@ -49,6 +85,7 @@ def zoom_output_shape(in_zyx, zoom_zyx):
     return tuple(int(v) for v in out)
 
 
+@device_guard
 def resample(src: torch.Tensor, out_shape, order: int = 3, *, src_z0: int = 0, src_shape=None,
              dst_z0: int = 0, dst_nz_local=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """Cubic B-spline (order=3) / trilinear (order=1) resample of ``src`` (sz,sy,sx) to
@@ -77,6 +114,7 @@ class OrderStats:
     """Device-resident state of the exact radix select (median + 99.9 percentile)."""
 
     def __init__(self, device):
+        self.device = torch.device(device)
         self.ws = torch.zeros(lib.mica_select_workspace_bytes(), dtype=torch.uint8, device=device)
         self._p = C.c_void_p(self.ws.data_ptr())
 
@@ -85,6 +123,7 @@ class OrderStats:
         off = lib.mica_select_hist_ptr(self._p) - self.ws.data_ptr()
         return self.ws[off:off + 8 * _lib.SELECT_HIST_WORDS].view(torch.int64)
 
+    @device_guard
     def run(self, x: torch.Tensor, n_total: int | None = None, all_reduce=None, peer=None):
         """Multi-GPU: the histograms of all ranks are summed between hist and pick, either by
         ``peer`` (a peer.PeerHistogram: one fused kernel over NVLink peer memory) or by
@@ -108,6 +147,7 @@ class OrderStats:
             check(lib.mica_select_pick(self._p, r, st), 'select_pick')
         return self
 
+    @device_guard
     def result(self):
         """(median, p999, n_pos, status) -- synchronises the stream."""
         med, p, npos, status = C.c_float(), C.c_float(), C.c_int64(), C.c_int()
@@ -115,6 +155,7 @@ class OrderStats:
                                      _stream()), 'select_result')
         return np.float32(med.value), np.float32(p.value), int(npos.value), int(status.value)
 
+    @device_guard
     def result_async(self, record: torch.Tensor | None = None) -> torch.Tensor:
         """Enqueue the copy of the 32-byte result record into pinned host memory (no synchronisation);
         decode it with ``OrderStats.decode`` once the stream has passed this point."""
@@ -131,6 +172,7 @@ class OrderStats:
         med, p = raw[16:24].view(np.float32)
         return np.float32(med), np.float32(p), n_pos, int(raw[28:32].view(np.int32)[0])
 
+    @device_guard
     def apply(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         p_x = _dev(x, torch.float32, 'x')
         if out is None:
@@ -140,6 +182,7 @@ class OrderStats:
         return out
 
 
+@device_guard
 def normalize(x: torch.Tensor, inplace: bool = False):
     """utils/preprocessing.py:122-133 on the device.  Returns (normalised, OrderStats)."""
     st = OrderStats(x.device).run(x)
@@ -147,6 +190,7 @@ def normalize(x: torch.Tensor, inplace: bool = False):
 
 
 # ---------------------------------------------------------------- R4 AF3 encode
+@device_guard
 def af3_encode(coords: torch.Tensor, bb_ch: torch.Tensor, aa_ch: torch.Tensor, origin_xyz, shape_zyx,
                clip_hi_xyz=None, *, z0: int = 0, nz_local=None, out: torch.Tensor | None = None):
     """24-channel rasteriser.  ``clip_hi_xyz`` defaults to the reference's (quirky)
@@ -180,13 +224,13 @@ class Af3CubeFiller:
     def __init__(self, device, n_slots, grid_size=48, padding=8, perm=(2, 1, 0)):
         self.device, self.n_slots = device, int(n_slots)
         self.grid_size, self.padding, self.perm = int(grid_size), int(padding), tuple(perm)
-        W = self.grid_size + 2 * self.padding
-        self.buffer = torch.zeros((self.n_slots, 24, W, W, W), dtype=torch.float32, device=device)
+        self.buffer = None          # [n_slots,24,W,W,W], allocated (zeroed) by the first fill
         self.status = torch.zeros(1, dtype=torch.int32, device=device)
         self.ws = None
         self._geom = None
         self._shown = None          # the ijk tensor whose cubes the slots currently show (kept alive)
 
+    @device_guard
     def _fill(self, ijk, nonzero_ptr):
         n_atoms, (nz, ny, nx) = self._geom
         prev = self._shown
@@ -202,10 +246,11 @@ class Af3CubeFiller:
 
     def clear(self):
         """Un-scatter every slot (buffer back to all zeros)."""
-        if self._shown is not None and self.ws is not None:
+        if self._shown is not None and self.ws is not None and self.buffer is not None:
             self._fill(None, None)
         self._shown = None
 
+    @device_guard
     def bin(self, coords, bb_ch, aa_ch, origin_xyz, shape_zyx, clip_hi_xyz=None):
         """Bin the atoms per cube (global cube grid of ``shape_zyx``).  Returns the device
         status word (1 == the reference's IndexError path, as af3_encode)."""
@@ -244,6 +289,9 @@ class Af3CubeFiller:
             raise _lib.MicaError('Af3CubeFiller.fill before bin')
         p_nz = _dev(nonzero, torch.int32, 'nonzero') if nonzero is not None else None
         _dev(ijk, torch.int32, 'ijk')
+        if self.buffer is None:
+            W = self.grid_size + 2 * self.padding
+            self.buffer = torch.zeros((self.n_slots, 24, W, W, W), dtype=torch.float32, device=self.device)
         self._fill(ijk, p_nz)
         return self.buffer[:B]
 
@@ -260,6 +308,7 @@ def cube_origins(cube_shape, grid_size):
     return np.ascontiguousarray(g)
 
 
+@device_guard
 def extract_cubes(vol: torch.Tensor, ijk: torch.Tensor, grid_size: int = 48, padding: int = 8,
                   perm=STANDARD_PERM, *, global_nz=None, z0: int = 0, out: torch.Tensor | None = None,
                   nonzero: torch.Tensor | None = None, cube_max: torch.Tensor | None = None):
@@ -296,6 +345,7 @@ class StitchedVolumes:
 
     def __init__(self, cube_shape, device, org=None, ext=None):
         self.shape = tuple(int(v) for v in cube_shape)
+        self.device = torch.device(device)
         self.org = tuple(org) if org is not None else (0, 0, 0)
         self.ext = tuple(ext) if ext is not None else self.shape
         e = self.ext
@@ -304,11 +354,32 @@ class StitchedVolumes:
         self.amino_acid_prediction = torch.zeros(e, dtype=torch.float32, device=device)
         self.amino_acid_probability = torch.zeros((20,) + e, dtype=torch.float32, device=device)
 
+    @classmethod
+    def from_block(cls, block: torch.Tensor, cube_shape, org, ext):
+        """Volumes that live in ONE caller-owned float32 block of 23 * prod(ext) elements, laid out
+        [backbone | carbon_alpha | amino_acid_prediction | amino_acid_probability x 20] -- the layout
+        ``postproc_stitch_peer`` writes into a rank's exported memory."""
+        self = cls.__new__(cls)
+        self.shape = tuple(int(v) for v in cube_shape)
+        self.device = block.device
+        self.org, self.ext = tuple(int(v) for v in org), tuple(int(v) for v in ext)
+        n = self.ext[0] * self.ext[1] * self.ext[2]
+        if block.dtype != torch.float32 or block.numel() < 23 * n or not block.is_contiguous():
+            raise _lib.MicaError('from_block needs a contiguous float32 block of 23 * prod(ext) elements')
+        flat = block.view(-1)
+        self.backbone_probability = flat[0:n].view(self.ext)
+        self.carbon_alpha_probability = flat[n:2 * n].view(self.ext)
+        self.amino_acid_prediction = flat[2 * n:3 * n].view(self.ext)
+        self.amino_acid_probability = flat[3 * n:23 * n].view((20,) + self.ext)
+        self.block = block
+        return self
+
     def as_dict(self):
         return {k: getattr(self, k) for k in ('backbone_probability', 'carbon_alpha_probability',
                                               'amino_acid_prediction', 'amino_acid_probability')}
 
 
+@device_guard
 def postproc_stitch(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: torch.Tensor,
                     vols: StitchedVolumes, grid_size: int = 48, padding: int = 8):
     """Fused utils/predict.py:342-349 + :494-501 for one batch of cubes."""
@@ -328,6 +399,27 @@ def postproc_stitch(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: t
     return vols
 
 
+@device_guard
+def postproc_stitch_peer(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: torch.Tensor, cube_shape,
+                         owner_table: torch.Tensor, x_bounds, grid_size: int = 48, padding: int = 8):
+    """``postproc_stitch`` for one map whose cubes are dealt out over several GPUs: every core plane goes to
+    the volume block of the rank that owns its x range (``owner_table``: int64 device tensor of ``world``
+    base pointers, ``peer.PeerVolumes.table``; ``x_bounds``: world + 1 plane bounds), local or over NVLink."""
+    B = ijk.shape[0]
+    W = grid_size + 2 * padding
+    for t, c, name in ((bb, 4, 'bb'), (ca, 4, 'ca'), (aa, 21, 'aa')):
+        if tuple(t.shape) != (B, c, W, W, W):
+            raise _lib.MicaError(f'{name} logits must be [{B},{c},{W},{W},{W}], got {tuple(t.shape)}')
+    X, Y, Z = (int(v) for v in cube_shape)
+    world = int(owner_table.numel())
+    bounds = (C.c_int * (world + 1))(*[int(v) for v in x_bounds])
+    check(lib.mica_postproc_stitch_peer(
+        _dev(bb, torch.float32, 'bb'), _dev(ca, torch.float32, 'ca'), _dev(aa, torch.float32, 'aa'),
+        _dev(ijk, torch.int32, 'ijk'), B, X, Y, Z, grid_size, padding,
+        _dev(owner_table, torch.int64, 'owner_table'), bounds, world, _stream()), 'postproc_stitch_peer')
+
+
+@device_guard
 def stitch_cubes(cubes: torch.Tensor, ijk: torch.Tensor, cube_shape, grid_size: int = 48, padding: int = 8,
                  org=None, ext=None, out: torch.Tensor | None = None):
     """reconstruct_volume alone (utils/predict.py:494-501): cubes [B,C,W,W,W] -> [C,ext...]."""

@@ -12,6 +12,7 @@ preprocessing.py, create_grids.py, predict.py) are thin shells over this class.
 """
 from __future__ import annotations
 
+import functools
 import time
 from contextlib import contextmanager
 from dataclasses import dataclass
@@ -93,6 +94,63 @@ def _no_timer(name):
     yield
 
 
+def _on_device(method):
+    """Run a pipeline method with the pipeline's GPU current (events, side streams and the C ABI all
+    act on the CUDA runtime's current device)."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kw):
+        if self.device.index is None or self.device.index == torch.cuda.current_device():
+            return method(self, *args, **kw)
+        with torch.cuda.device(self.device):
+            return method(self, *args, **kw)
+    return wrapper
+
+
+D8_MODES = ('none', 'split', 'reference')
+
+
+def _f32c(t):
+    """Logits as the stitch kernel wants them (contiguous float32); a no-op for tensors that already are."""
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def run_model_chunks(model_fn, x, af, flags_host, ijk, stitch, model_batch=None, d8='none'):
+    """Feed one super-batch of cubes to ``model_fn`` the way the reference feeds MICA.forward, and hand
+    every result to ``stitch(bb, ca, aa, ijk_chunk)``.
+
+    ``model_batch``: cubes per model call (the reference: 1 up to 200 cubes, else <= 8,
+    utils/predict.py:156-215); None = the whole super-batch in one call.
+    ``d8``: MICA.forward decides ``is_af_zero = af_features.abs().sum() < 1e-6`` over the WHOLE batch
+    (models/model.py:60-63), so a cube without AF3 signal gets different logits when it shares a batch
+    with one that has some.
+      'split'      every model call sees either only zero-AF3 cubes or only non-zero ones
+                   (``flags_host[b] != 0`` = cube b has AF3 signal): each cube gets what the reference's
+                   single-sample mode gives it, whatever it is batched with;
+      'reference'  consecutive cubes are batched as they come, mixed -- the reference's batched mode;
+      'none'       same as 'reference' (for stand-in models without that branch)."""
+    if d8 not in D8_MODES:
+        raise MicaError(f'd8 must be one of {D8_MODES}, got {d8!r}')
+    B = int(x.shape[0])
+    mb = B if model_batch is None else max(1, int(model_batch))
+    for c0 in range(0, B, mb):
+        c1 = min(B, c0 + mb)
+        groups = [None]
+        if d8 == 'split' and c1 - c0 > 1:
+            f = np.asarray(flags_host[c0:c1]) != 0
+            if f.any() and not f.all():
+                groups = [np.flatnonzero(f), np.flatnonzero(~f)]
+        for g in groups:
+            if g is None:
+                gx, gaf, gijk = x[c0:c1], af[c0:c1], ijk[c0:c1]
+            else:
+                idx = torch.as_tensor(g + c0, device=x.device)
+                gx, gaf, gijk = x[idx], af[idx], ijk[idx].contiguous()
+            bb, ca, aa = model_fn(gx, gaf)
+            stitch(bb, ca, aa, gijk)
+
+
 class MapPipeline:
     """One GPU's share of the hot path.  With ``slab`` left None it owns the whole map."""
 
@@ -108,6 +166,7 @@ class MapPipeline:
         self.normalized = None          # [nz,ny,nx] float32, device
         self.af3 = None                 # [24,nz,ny,nx] float32, device (None -> zero AF3 features)
         self.stats = None
+        self._stats = None
         self.norm_status = None
         self._x, self._af, self._nz = [None, None], [None, None], [None, None]
         self.timer = _no_timer      # bench.py swaps in a StageTimer
@@ -128,7 +187,35 @@ class MapPipeline:
         self._pinned_free = []          # (order-stats record, AF3 status word) pairs in pinned memory, reused:
         self._pre_stream = None         # cudaHostAlloc synchronises the device, so never allocate per step
 
+    def configure(self, grid_size=None, padding=None, batch_cubes=None, order=None, target_voxel_size=None):
+        """Change the cube geometry / batch size of a live pipeline (the drop-in classes learn them stage
+        by stage: ``GridCreator`` is told grid_size and padding after ``DataPreprocessor`` has already
+        normalised the map).  Buffers that depend on what changed are dropped and rebuilt on demand."""
+        gs = self.grid_size if grid_size is None else int(grid_size)
+        pad = self.padding if padding is None else int(padding)
+        bc = self.batch_cubes if batch_cubes is None else int(batch_cubes)
+        if order is not None:
+            self.order = int(order)
+        if target_voxel_size is not None:
+            self.target_voxel_size = target_voxel_size
+        if (gs, pad, bc) != (self.grid_size, self.padding, self.batch_cubes):
+            if gs + 2 * pad != self.window or bc > self.batch_cubes:
+                self._x, self._af, self._nz = [None, None], [None, None], [None, None]
+            if (gs, pad) != (self.grid_size, self.padding) or bc > self.batch_cubes:
+                self._fillers, self._bins, self._atoms_binned = [None, None], None, False
+            self.grid_size, self.padding, self.batch_cubes = gs, pad, bc
+            self.window = gs + 2 * pad
+            self._ijk_key = None
+        return self
+
+    def release_map(self):
+        """Forget the current map (normalised volume, dense AF3 volume, atom bins stay allocated but
+        unused): lets the caller's session drop its HBM."""
+        self.normalized, self.af3 = None, None
+        self._atoms_binned = False
+
     # ------------------------------------------------------------------ stage 1+2
+    @_on_device
     def resample_and_normalize(self, src: torch.Tensor, header: MapHeader | None = None, defer_status=False):
         """utils/preprocessing.py:98-133 on the device.  Returns True on success; on the
         reference's two failure modes (:152-157) returns False and leaves ``normalized`` None.
@@ -144,12 +231,21 @@ class MapPipeline:
             else:
                 res = ops.resample(src, out_shape, order=self.order)
         with self.timer('order_stats'):
-            self.stats = ops.OrderStats(self.device).run(res)
+            self.stats = self._order_stats().run(res)
         with self.timer('normalize_apply'):
             self.normalized = self.stats.apply(res, res)       # in place: the resampled map is not kept
         self.norm_status = None
         return True if defer_status else self.check_status()
 
+    def _order_stats(self):
+        """The select workspace lives as long as the pipeline (allocating and zero-filling it per map
+        cost a cudaMalloc-class call on the B <= 8 drop-in path); every run re-initialises it in
+        stream order."""
+        if self._stats is None:
+            self._stats = ops.OrderStats(self.device)
+        return self._stats
+
+    @_on_device
     def check_status(self):
         med, p, npos, status = self.stats.result()
         self.norm_status = status
@@ -164,6 +260,7 @@ class MapPipeline:
         self.normalized = norm
 
     # -------------------------------------------------------------------- stage 3
+    @_on_device
     def encode_af3(self, coords: torch.Tensor, bb_ch: torch.Tensor, aa_ch: torch.Tensor, defer_status=False):
         """utils/preprocessing.py:268-298.  Returns True iff the reference would have
         succeeded (no IndexError from the mis-ordered clip, D7)."""
@@ -235,6 +332,7 @@ class MapPipeline:
     def _extract_af3(self, ijk, af, nonzero):
         ops.extract_cubes(self.af3, ijk, self.grid_size, self.padding, self.perm, out=af, nonzero=nonzero)
 
+    @_on_device
     def extract_batch(self, b0: int, b1: int, want_flags: bool = False, slot: int = 0):
         """Cubes [b0,b1) -> (exp_map [B,1,W,W,W], af_features [B,24,W,W,W][, nonzero flags])
         -- the two tensors MICA.forward takes (models/model.py:331).  ``slot`` picks one of
@@ -261,28 +359,57 @@ class MapPipeline:
         return ops.StitchedVolumes(self.cube_shape, self.device)
 
     # ---------------------------------------------------------------- stage 5 (+model)
-    def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None, on_batch=None):
+    @_on_device
+    def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None, on_batch=None, *,
+                           model_batch=None, d8='none', order=None, stitch_fn=None):
         """run_inference + reconstruct_volume (utils/predict.py:307-587) without the
         per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits, enqueued
         on the current stream.  With ``prefetch`` the cubes of batch n+1 are cut on a side
         stream while the model and the softmax/argmax + stitch of batch n run.
         ``on_batch(vols, n_done)`` is called after the stitch of each batch has been enqueued
-        (``n_done`` cubes of ``ijk_host`` are then final in ``vols``, in stream order)."""
+        (``n_done`` cubes of ``ijk_host`` are then final in ``vols``, in stream order).
+
+        Cubes are cut ``batch_cubes`` at a time (one launch per stage); ``model_batch`` / ``d8`` say how
+        such a super-batch is fed to the model (``run_model_chunks``: the reference's batches of <= 8 and
+        its whole-batch zero-AF3 test, D8).  ``order``: a permutation of the cube indices (the reference
+        visits cubes in ``glob`` order, utils/predict.py:269); default = the i-major loop order of
+        utils/create_grids.py:143-145.  ``stitch_fn(bb, ca, aa, ijk, vols)`` replaces the local
+        softmax/argmax + stitch (multi-GPU: cores owned by another rank go to its volumes)."""
         if self.normalized is None:
             raise MicaError('no normalised map')
         self.cube_index()
         if vols is None:
             vols = self._new_volumes()
+        self._custom_order = order is not None
+        if order is not None:
+            order = np.asarray(order, dtype=np.int64)
+            self._set_cube_origins(self.ijk_host[order], ('ordered', id(order), len(order)))
+            self._ijk_key = None                          # the next map starts from the loop order again
         n = len(self.ijk_host)
         batches = [(b0, min(n, b0 + self.batch_cubes)) for b0 in range(0, n, self.batch_cubes)]
         if not batches:
             return vols
+        want_flags = d8 == 'split' and (model_batch is None or int(model_batch) > 1)
+        if stitch_fn is None:
+            def stitch_fn(bb, ca, aa, ijk, vols_):
+                ops.postproc_stitch(bb, ca, aa, ijk, vols_, self.grid_size, self.padding)
+
+        def stitch(bb, ca, aa, ijk):
+            with self.timer('postproc_stitch'):
+                stitch_fn(_f32c(bb), _f32c(ca), _f32c(aa), ijk, vols)
+
+        def consume(cur, b0, b1):
+            flags = None
+            if want_flags:
+                x, af, nzf = cur
+                flags = nzf.cpu().numpy()                 # waits for the cut of this batch (it has to be there anyway)
+            else:
+                x, af = cur[0], cur[1]
+            run_model_chunks(model_fn, x, af, flags, self.ijk[b0:b1], stitch, model_batch, d8)
+
         if not self.prefetch or len(batches) == 1:
             for b0, b1 in batches:
-                x, af = self.extract_batch(b0, b1)
-                bb, ca, aa = model_fn(x, af)
-                with self.timer('postproc_stitch'):
-                    ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
+                consume(self.extract_batch(b0, b1, want_flags=want_flags), b0, b1)
                 if on_batch is not None:
                     on_batch(vols, b1)
             return vols
@@ -300,7 +427,7 @@ class MapPipeline:
             with torch.cuda.stream(pre):
                 if consumed[slot] is not None:
                     pre.wait_event(consumed[slot])           # the model has read this buffer's last batch
-                out = self.extract_batch(*batches[i], slot=slot)
+                out = self.extract_batch(*batches[i], want_flags=want_flags, slot=slot)
                 ready[slot] = torch.cuda.Event()
                 ready[slot].record(pre)
             return out
@@ -309,17 +436,16 @@ class MapPipeline:
         for i, (b0, b1) in enumerate(batches):
             nxt = cut(i + 1) if i + 1 < len(batches) else None
             main.wait_event(ready[i & 1])
-            bb, ca, aa = model_fn(*cur)
+            consume(cur, b0, b1)
             consumed[i & 1] = torch.cuda.Event()
             consumed[i & 1].record(main)
-            with self.timer('postproc_stitch'):
-                ops.postproc_stitch(bb, ca, aa, self.ijk[b0:b1], vols, self.grid_size, self.padding)
             if on_batch is not None:
                 on_batch(vols, b1)
             cur = nxt
         self.last_loop_enqueue_ms = (time.perf_counter() - t_enqueue) * 1e3     # host side of the batch loop
         return vols
 
+    @_on_device
     def finish(self):
         """Wait for every ``run(..., defer_check=True)`` issued so far and raise if one of them failed."""
         pending, self._deferred = self._deferred, []
@@ -334,7 +460,8 @@ class MapPipeline:
                 raise MicaError('AF3 encoding failed: atom index outside the grid (reference IndexError path, D7)')
 
     # ------------------------------------------------------------------ whole path
-    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False):
+    @_on_device
+    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False, **predict_kw):
         """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
         device tensors or None.  Raises on the reference's normalisation failures -- at once, or,
         with ``defer_check``, from ``finish()``: the status words are copied to pinned memory in
@@ -346,7 +473,7 @@ class MapPipeline:
             self.encode_af3(*atoms, defer_status=True)
         else:
             self.af3, self._atoms_binned = None, False
-        vols = self.predict_and_stitch(model_fn, vols, on_batch)
+        vols = self.predict_and_stitch(model_fn, vols, on_batch, **predict_kw)       # model_batch / d8 / order
         if defer_check:
             if self._pinned_free:
                 rec, af = self._pinned_free.pop()
@@ -384,6 +511,8 @@ class _SlabDrain:
     def __call__(self, vols, n_done):
         ijk = self.pipe.ijk_host
         n = len(ijk)
+        if getattr(self.pipe, '_custom_order', False) and n_done < n:
+            return                                 # cubes not in loop order: nothing is known final before the end
         # i-layers whose last cube has been stitched
         if n_done >= n:
             layer_end = vols.ext[0]
@@ -445,3 +574,22 @@ def run_map_pipeline_host(src_host: torch.Tensor, header: MapHeader, atoms_host,
         d2h += v.numel() * v.element_size()
     torch.cuda.current_stream().synchronize()
     return out, h2d, d2h
+
+
+_SHARED: dict = {}
+
+
+def shared_pipeline(device) -> MapPipeline:
+    """One long-lived MapPipeline per GPU and process: the drop-in classes (DataPreprocessor ->
+    GridCreator -> CryoEMPredictor) run consecutive maps through it, so the cube buffers, the select
+    workspace, the atom bins and the side stream are allocated once, not per map."""
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise MicaError(f'mica_b200 needs a CUDA device, got {device!r} (there is no CPU fallback)')
+    if dev.index is None:
+        ops.require_gpu()
+        dev = torch.device('cuda', torch.cuda.current_device())
+    pipe = _SHARED.get(dev.index)
+    if pipe is None:
+        pipe = _SHARED[dev.index] = MapPipeline(dev)
+    return pipe

@@ -3,35 +3,125 @@
 Same constructor and ``run_prediction() -> (bool, {four volumes})`` contract
 (utils/predict.py:48,589; consumer: Solver.nnPred, utils/modeler.py:722-734).  The
 model (models/model.py::MICA, PyTorch convolutions) is used as it is; everything
-around it -- cube assembly, softmax/argmax, stitching -- runs in libmica_b200.so with
-no per-cube file: cubes come from the volumes GridCreator registered (or, when only
-the reference's .npz files exist on disk, are uploaded from them)."""
+around it -- cube assembly, softmax/argmax, stitching -- runs in libmica_b200.so on the
+``MapPipeline`` that DataPreprocessor / GridCreator prepared (``MapPipeline.predict_and_stitch``,
+the path ``bench.py`` measures): cubes are cut 256 at a time on a side stream into reused
+buffers, the AF3 channels are rasterised straight from the docked atoms, the model is fed in the
+reference's batches (1, or <= 8 above 200 cubes), its logits are post-processed and their cores
+pasted into the four volumes, and finished layers of the volumes stream to pinned host memory
+while later cubes are still in the model.  When only the reference's ``.npz`` files exist on
+disk, the cubes are uploaded from them instead."""
 from __future__ import annotations
 
 import glob
 import logging
 import os
+import re
 import time
 
 import numpy as np
 import torch
 
 from . import ops, pdb, session
+from .pipeline import MapPipeline, _SlabDrain, run_model_chunks, shared_pipeline
 
 MAP_TYPES = ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction',
              'amino_acid_probability')
+SMALL_VOLUMES = MAP_TYPES[:3]
+
+
+class HostPool:
+    """Pinned host buffers for the stitched volumes, reused from map to map (``cudaHostAlloc`` of the
+    10 GB a 480^3 map returns costs seconds and synchronises the device).  Arrays handed out for one
+    map are overwritten by the next map that uses the same pool -- pass a pool only when the previous
+    map's volumes are no longer needed; without one every predictor allocates its own buffers."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32):
+        shape = tuple(int(v) for v in shape)
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = self._bufs[name] = torch.empty(shape, dtype=dtype).pin_memory()
+        return t
+
+
+class DeviceVolume:
+    """A stitched volume that stayed in HBM, usable where the reference expects the NumPy array:
+    ``shape`` / ``dtype`` / indexing / ``np.asarray`` work, a full host copy is made (once) only when
+    something asks for all of it.  ``mica_b200.candidates`` takes ``.tensor`` and never copies --
+    ``amino_acid_probability`` is 20 of the 23 output channels and its only consumer in the reference is a
+    gather at the picked C-alpha voxels (utils/modeler.py:850)."""
+
+    def __init__(self, tensor: torch.Tensor):
+        self.tensor = tensor
+        self._host = None
+
+    shape = property(lambda self: tuple(self.tensor.shape))
+    ndim = property(lambda self: self.tensor.dim())
+    size = property(lambda self: self.tensor.numel())
+    dtype = property(lambda self: np.dtype(np.float32))
+
+    def __len__(self):
+        return self.tensor.shape[0]
+
+    def numpy(self):
+        if self._host is None:
+            self._host = self.tensor.cpu().numpy()
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+    def __getitem__(self, idx):
+        if self._host is not None:
+            return self._host[idx]
+        dev = self.tensor.device
+
+        def conv(i):
+            if isinstance(i, np.ndarray):
+                return torch.from_numpy(np.ascontiguousarray(i)).to(dev)
+            if isinstance(i, (list,)):
+                return torch.as_tensor(i, device=dev)
+            if isinstance(i, np.integer):
+                return int(i)
+            return i
+        tidx = tuple(conv(i) for i in idx) if isinstance(idx, tuple) else conv(idx)
+        out = self.tensor[tidx]
+        return out.cpu().numpy() if out.dim() else np.float32(out.item())
 
 
 class CryoEMPredictor:
     def __init__(self, model_path, grids_path, output_path, save_output=True, device='cuda', quiet=False,
-                 model=None, keep_on_device=False, host_volumes=MAP_TYPES):
-        """``keep_on_device`` / ``host_volumes`` are additions to the reference signature: with
-        ``keep_on_device`` the stitched volumes stay registered in HBM (``session`` key
-        ``<output_path>/results/device_volumes``) for ``mica_b200.candidates.clustering_head``, and
-        ``host_volumes`` names the volumes copied to the host (default: all four, as the reference returns);
-        leaving out ``amino_acid_probability`` saves 20 of the 23 channels of PCIe traffic."""
+                 model=None, keep_on_device=True, host_volumes=None, host_pool=None, reference_batching=False,
+                 super_batch=256, release_inputs=True):
+        """Additions to the reference signature (all optional):
+
+        ``model``               an already loaded model (callable ``(exp_map, af_features) -> (bb, ca, aa)``).
+        ``host_volumes``        the volumes copied to the host as NumPy arrays.  Default: the three
+                                single-channel volumes; ``amino_acid_probability`` is returned as a
+                                ``DeviceVolume`` (array-like, downloads itself when read as a whole).
+                                ``MAP_TYPES`` returns four NumPy arrays exactly as the reference does.
+        ``keep_on_device``      keep the four device volumes registered (``session`` key
+                                ``<output_path>/results/device_volumes``) for ``mica_b200.candidates``.
+        ``host_pool``           a ``HostPool`` whose pinned buffers receive the host volumes (reused from map
+                                to map); default: fresh pinned buffers per predictor.
+        ``reference_batching``  D8: False (default) never lets a cube without AF3 signal share a model call
+                                with one that has some, so every cube gets the logits of the reference's
+                                single-sample mode whatever the batch size; True reproduces the reference's
+                                batched mode literally -- cubes in ``glob`` order (utils/predict.py:269) when
+                                the grid files exist, mixed batches of ``optimal_batch_size``.
+        ``super_batch``         cubes cut / stitched per kernel launch.
+        ``release_inputs``      drop the consumed session entries (normalised map, atoms, cube indices) when
+                                done, as Solver.nnPred deletes the files (utils/modeler.py:753-758)."""
         self.keep_on_device = bool(keep_on_device)
-        self.host_volumes = tuple(host_volumes)
+        self.host_volumes = SMALL_VOLUMES if host_volumes is None else tuple(host_volumes)
+        self.host_pool = host_pool
+        self.reference_batching = bool(reference_batching)
+        self.super_batch = int(super_batch)
+        self.release_inputs = bool(release_inputs)
         self.model_path = model_path
         self.grids_path = grids_path
         self.output_path = output_path
@@ -131,27 +221,59 @@ class CryoEMPredictor:
             self.timing_stats['model_loading'] = time.time() - t0
 
     # ------------------------------------------------------------------ inference + stitch
-    def _batches(self, B):
-        n = self.sample_count
-        return [(b0, min(n, b0 + B)) for b0 in range(0, n, B)]
+    def _model_batch(self):
+        return self.optimal_batch_size if self.use_optimized_batching else 1
 
-    def _fetch(self, b0, b1, dev):
-        """(exp_map [B,1,W^3], af_features [B,24,W^3], nonzero flags [B]) on the device."""
+    def _reference_order(self):
+        """The cube order of the reference's DataLoader: ``glob.glob`` over the grid files
+        (utils/predict.py:269, shuffle=False) -- directory order, when the files exist; the creation
+        (loop) order otherwise.  Returns indices into the pipeline's cube list, or None."""
+        files = glob.glob(os.path.join(self._map_dir(), '*.npz'))
+        if not files:
+            return None
+        where = {tuple(int(v) for v in row): n for n, row in enumerate(self._source['ijk'])}
+        order = []
+        for f in files:
+            mt = re.search(r'_i(-?\d+)_j(-?\d+)_k(-?\d+)\.npz$', os.path.basename(f))
+            if mt is None or tuple(int(g) for g in mt.groups()) not in where:
+                return None
+            order.append(where[tuple(int(g) for g in mt.groups())])
+        return order if sorted(order) == list(range(len(where))) else None
+
+    def _pipeline(self, dev):
+        """The MapPipeline holding this map: the one DataPreprocessor started, else a fresh one around
+        the registered volume."""
         s = self._source
-        gs, pad = s['grid_size'], s['padding']
-        W = gs + 2 * pad
+        m, a = s['map'], s['af3']
+        pipe = m.get('pipe') or shared_pipeline(m['volume'].device)
+        n = len(s['ijk'])
+        pipe.configure(grid_size=s['grid_size'], padding=s['padding'], batch_cubes=max(1, min(self.super_batch, n)))
+        pipe.set_normalized(m['volume'], m['header'])
+        if a is not None and a.get('atoms') is not None:
+            if not pipe.encode_af3(*a['atoms']):            # bins for the final geometry; cannot fail if
+                raise IndexError('atom index outside the grid')    # create_AF3_encodings succeeded
+        elif a is not None:
+            vol = a['volume']
+            pipe.af3, pipe._atoms_binned = (vol.get() if hasattr(vol, 'get') else vol), False
+        else:
+            pipe.af3, pipe._atoms_binned = None, False      # dataset/dataset.py:218-219: zeros
+        return pipe
+
+    def _host_buffers(self, vols):
+        out = {}
+        for k, v in vols.as_dict().items():
+            if k in self.host_volumes:
+                out[k] = (self.host_pool.get(k, v.shape) if self.host_pool is not None
+                          else torch.empty(tuple(v.shape), dtype=v.dtype).pin_memory())
+        return out
+
+    def _fetch_files(self, b0, b1, dev):
+        """dataset/dataset.py:194-224 for the reference's .npz files: (exp_map, af_features, flags)."""
+        s = self._source
+        W = s['grid_size'] + 2 * s['padding']
         B = b1 - b0
-        if s['kind'] == 'resident':
-            ijk = self._ijk_dev[b0:b1]
-            x = ops.extract_cubes(s['map']['volume'], ijk, gs, pad, s['map']['perm'])
-            flags = torch.zeros(B, dtype=torch.int32, device=dev)
-            if s['af3'] is not None:
-                af = ops.extract_cubes(s['af3']['volume'], ijk, gs, pad, s['af3']['perm'], nonzero=flags)
-            else:
-                af = torch.zeros((B, 24, W, W, W), dtype=torch.float32, device=dev)
-            return x, af, flags
         xs, afs = [], []
-        for f in s['files'][b0:b1]:                              # dataset/dataset.py:194-224
+        for f in s['files'][b0:b1]:
             xs.append(np.load(f)['grid'])
             try:
                 feats = []
@@ -167,37 +289,61 @@ class CryoEMPredictor:
         return x, af, flags
 
     def run_inference_and_reconstruct(self):
-        """run_inference + reconstruct_volume (utils/predict.py:307-512) fused: logits are
-        post-processed and their cores pasted into the four volumes as each batch finishes."""
+        """run_inference + reconstruct_volume (utils/predict.py:307-512) fused.  Returns
+        (device volumes, {name: pinned host tensor})."""
         dev = torch.device(self.device)
         s = self._source
         gs, pad = s['grid_size'], s['padding']
-        self._ijk_dev = torch.from_numpy(np.ascontiguousarray(s['ijk'], dtype=np.int32)).to(dev)
-        vols = ops.StitchedVolumes(s['cube_shape'], dev)
-        B = self.optimal_batch_size if self.use_optimized_batching else 1
         model = self.model
         if hasattr(model, 'eval'):
             model.eval()
+        d8 = 'reference' if self.reference_batching else 'split'
         with torch.no_grad():
-            for b0, b1 in self._batches(B):
-                x, af, flags = self._fetch(b0, b1, dev)
-                ijk = self._ijk_dev[b0:b1]
-                if b1 - b0 == 1:
-                    groups = [torch.arange(1, device=dev)]
-                else:
-                    # D8: MICA tests `af_features.abs().sum() < 1e-6` over the whole batch
-                    # (models/model.py:60-63); cubes without AF3 signal get their own batch so the
-                    # result does not depend on what they happen to be batched with.
-                    nz = flags != 0
-                    groups = [g for g in (torch.nonzero(nz).flatten(), torch.nonzero(~nz).flatten()) if len(g)]
-                for g in groups:
-                    whole = len(g) == (b1 - b0)
-                    gx, gaf, gijk = (x, af, ijk) if whole else (x[g].contiguous(), af[g].contiguous(),
-                                                               ijk[g].contiguous())
-                    bb, ca, aa = model(gx, gaf)
-                    ops.postproc_stitch(bb.contiguous().float(), ca.contiguous().float(), aa.contiguous().float(),
-                                        gijk, vols, gs, pad)
-        return vols
+            if s['kind'] == 'resident':
+                pipe = self._pipeline(dev)
+                order = self._reference_order() if self.reference_batching else None
+                pipe.cube_index()
+                vols = pipe._new_volumes()
+                out_host = self._host_buffers(vols)
+                drain = _SlabDrain(pipe, out_host)
+                vols = pipe.predict_and_stitch(model, vols, on_batch=drain, model_batch=self._model_batch(),
+                                               d8=d8, order=order)
+                drain.finish()
+                torch.cuda.current_stream(pipe.device).synchronize()
+                self._pipe = pipe
+                return vols, out_host
+            # the reference's per-cube files: upload, then the same model feeding and stitching
+            if dev.type != 'cuda':
+                raise ops._lib.MicaError('mica_b200 has no CPU path')
+            ijk_dev = torch.from_numpy(np.ascontiguousarray(s['ijk'], dtype=np.int32)).to(dev)
+            vols = ops.StitchedVolumes(s['cube_shape'], dev)
+            step = max(self._model_batch(), 1) * 4
+            for b0 in range(0, self.sample_count, step):
+                b1 = min(self.sample_count, b0 + step)
+                x, af, flags = self._fetch_files(b0, b1, dev)
+                run_model_chunks(model, x, af, flags.cpu().numpy(), ijk_dev[b0:b1],
+                                 lambda bb, ca, aa, ijk: ops.postproc_stitch(
+                                     bb.contiguous().float(), ca.contiguous().float(), aa.contiguous().float(),
+                                     ijk, vols, gs, pad),
+                                 self._model_batch(), d8)
+            out_host = self._host_buffers(vols)
+            for k, t in out_host.items():
+                t.copy_(getattr(vols, k), non_blocking=True)
+            torch.cuda.synchronize(dev)
+            return vols, out_host
+
+    def _release(self):
+        s = self._source or {}
+        if s.get('kind') != 'resident':
+            return
+        for entry in (s['map'], s['af3']):
+            if entry is not None and entry.get('source') is not None:
+                session.drop(entry['source'])
+        session.drop(self._map_dir())
+        session.drop(self._af3_dir())
+        pipe = getattr(self, '_pipe', None)
+        if pipe is not None:
+            pipe.release_map()
 
     # utils/predict.py:589-634
     def run_prediction(self):
@@ -208,21 +354,24 @@ class CryoEMPredictor:
             if not self.load_model():
                 return False, {}
             t0 = time.time()
-            vols = self.run_inference_and_reconstruct()
-            torch.cuda.synchronize()
+            vols, out_host = self.run_inference_and_reconstruct()
             self.timing_stats['inference'] = time.time() - t0
             t0 = time.time()
+            dev_key = os.path.join(str(self.output_path), 'results', 'device_volumes')
             if self.keep_on_device:
-                session.put(os.path.join(str(self.output_path), 'results', 'device_volumes'), **vols.as_dict())
-            volumes = {k: v.cpu().numpy() for k, v in vols.as_dict().items() if k in self.host_volumes}
+                session.put(dev_key, **vols.as_dict())
+            volumes = {}
+            for k, v in vols.as_dict().items():
+                volumes[k] = out_host[k].numpy() if k in out_host else DeviceVolume(v)
             self.timing_stats['reconstruction'] = time.time() - t0
             if self.save_output:
                 t0 = time.time()
                 os.makedirs(self.reconstruction_path, exist_ok=True)
                 for k in MAP_TYPES:
-                    if k in volumes:
-                        np.save(f'{self.reconstruction_path}/{k}.npy', volumes[k])
+                    np.save(f'{self.reconstruction_path}/{k}.npy', np.asarray(volumes[k]))
                 self.timing_stats['saving'] = time.time() - t0
+            if self.release_inputs:
+                self._release()
             self.timing_stats['total'] = time.time() - t_total
             return True, volumes
         except Exception as e:                                   # reference: logged, (False, {}) (:632-634)

@@ -26,7 +26,7 @@ import torch
 
 from . import ops
 from ._lib import MicaError, NORM_OK
-from .pipeline import MapHeader, MapPipeline, zoom_factors
+from .pipeline import MapHeader, MapPipeline, zoom_factors, _on_device
 
 
 def _split_even(n_items: int, parts: int):
@@ -63,8 +63,15 @@ class SlabPlan:
         sz, nz = self.src_shape[0], self.out_shape[0]
         layers = -(-nz // self.grid_size)
         lb = _split_even(layers, self.world)
-        ob = _split_even(sz, self.world)
         scale = (sz - 1) / (nz - 1) if nz > 1 else 1.0
+        # a rank HOLDS the source planes under its output slab (not an even split of the source): what it
+        # still needs from others is then only the taps + prefilter horizon + cube halo just beyond its
+        # block, i.e. planes of its two direct neighbours (the peer-memory halo exchange relies on that)
+        ob = [0]
+        for r in range(1, self.world):
+            o = min(nz, lb[r] * self.grid_size)
+            ob.append(sz if o >= nz else max(ob[-1], min(sz, int(round(o * scale)))))
+        ob.append(sz)
         taps_lo, taps_hi = (1, 2) if order == 3 else (0, 1)
         k = self.halo_k if (order == 3 and not self.identity) else 0
         self.ranks = []
@@ -128,11 +135,18 @@ class SlabPipeline(MapPipeline):
 
     def __init__(self, device, rank, world, grid_size=48, padding=8, order=3, batch_cubes=16,
                  target_voxel_size=1.0, halo_k=16, global_src_shape=None, group=None, af3_mode='sparse',
-                 hist_exchange='peer'):
+                 hist_exchange='peer', halo_exchange='peer'):
         super().__init__(device, grid_size, padding, order, batch_cubes, target_voxel_size, af3_mode)
         self.rank, self.world, self.halo_k, self.group = int(rank), int(world), halo_k, group
         self.global_src_shape = global_src_shape
         self.plan = None
+        #: 'peer' = publish / pull kernels over NVLink peer memory (peer.PeerHalo, built on first use; plans
+        #: that reach beyond the direct neighbours fall back to NCCL); 'nccl' = batch_isend_irecv
+        if halo_exchange not in ('peer', 'nccl'):
+            raise MicaError(f'halo_exchange must be peer or nccl, got {halo_exchange!r}')
+        self.halo_exchange = halo_exchange
+        self.peer_halo = None
+        self._plan_key = None
         #: 'peer' = one fused publish/signal/wait/sum kernel over NVLink peer memory per radix round
         #: (peer.PeerHistogram, built on first use); 'nccl' = torch.distributed.all_reduce
         if hist_exchange not in ('peer', 'nccl'):
@@ -151,17 +165,47 @@ class SlabPipeline(MapPipeline):
         import torch.distributed as dist
         dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _halo_slot_elems(self, plan):
+        """Largest halo (float32 elements) any rank receives from one neighbour, or None when some rank
+        needs planes from beyond its direct neighbours.  Global: the same answer on every rank."""
+        from .peer import PeerHalo
+        planes = 0
+        for r in range(self.world):
+            np_ = PeerHalo.neighbour_plan(plan, r)
+            if np_ is None:
+                return None
+            planes = max([planes] + [rng[1] - rng[0] for rng in np_ if rng is not None])
+        return planes * plan.src_shape[1] * plan.src_shape[2]
+
     def _exchange(self, own):
+        if self.halo_exchange == 'peer' and self.world > 1:
+            need = self._halo_slot_elems(self.plan)      # the same on every rank (the plan is global)
+            if need is not None:
+                from .peer import PeerHalo
+                if self.peer_halo is None or self.peer_halo.slot_elems < need:
+                    if self.peer_halo is not None:
+                        self.peer_halo.close()
+                    self.peer_halo = self._make_peer_halo(need)
+                return self.peer_halo.exchange(own, self.plan)
         return exchange_source_halo(own, self.plan, self.rank, self.group)
+
+    def _make_peer_halo(self, slot_elems):
+        from .peer import PeerHalo
+        return PeerHalo(self.device, self.rank, self.world, slot_elems, self.group)
 
     def make_plan(self, own_shape, header):
         gshape = self.global_src_shape
         if gshape is None:                      # weak-scaling default: equal blocks stacked along z
             gshape = (own_shape[0] * self.world, own_shape[1], own_shape[2])
-        self.plan = SlabPlan(gshape, header.voxel_size, self.grid_size, self.padding, self.world,
-                             self.target_voxel_size, self.halo_k, self.order)
+        key = (tuple(gshape), tuple(float(v) for v in header.voxel_size), self.grid_size, self.padding, self.world,
+               float(self.target_voxel_size), self.halo_k, self.order)
+        if key != self._plan_key:               # host arithmetic only, but it runs once per map otherwise
+            self.plan = SlabPlan(gshape, header.voxel_size, self.grid_size, self.padding, self.world,
+                                 self.target_voxel_size, self.halo_k, self.order)
+            self._plan_key = key
         return self.plan
 
+    @_on_device
     def slab_resample(self, own_src, header=None):
         """Halo exchange + resample of this rank's planes.  Returns (res, owned): the local
         resampled planes [ext_lo, ext_hi) and the view of the owned ones [out_lo, out_hi)."""
@@ -188,14 +232,15 @@ class SlabPipeline(MapPipeline):
             self.normalized = self.stats.apply(res, res)
         self.norm_status = None
 
+    @_on_device
     def resample_and_normalize(self, own_src, header=None, defer_status=False):
         res, owned = self.slab_resample(own_src, header)
         nz, ny, nx = self.plan.out_shape
         with self.timer('order_stats'):
             if self.hist_exchange == 'peer' and self.world > 1:
-                self.stats = ops.OrderStats(self.device).run(owned, n_total=nz * ny * nx, peer=self._peer_group())
+                self.stats = self._order_stats().run(owned, n_total=nz * ny * nx, peer=self._peer_group())
             else:
-                self.stats = ops.OrderStats(self.device).run(owned, n_total=nz * ny * nx,
+                self.stats = self._order_stats().run(owned, n_total=nz * ny * nx,
                                                              all_reduce=self._all_reduce_hist)
         self.slab_normalize(res)
         return True if defer_status else self.check_status()
@@ -203,6 +248,20 @@ class SlabPipeline(MapPipeline):
     def _global_shape(self):
         return tuple(self.plan.out_shape)
 
+    def _check_halo(self):
+        if self.peer_halo is not None and self.peer_halo.timed_out():
+            raise MicaError('halo exchange timed out: a neighbouring rank never published its source planes')
+
+    def check_status(self):
+        ok = super().check_status()
+        self._check_halo()
+        return ok
+
+    def finish(self):
+        super().finish()
+        self._check_halo()
+
+    @_on_device
     def encode_af3(self, coords, bb_ch, aa_ch, defer_status=False):
         if self.af3_mode == 'sparse':            # atoms are binned on the global cube grid
             return super().encode_af3(coords, bb_ch, aa_ch, defer_status)
@@ -241,3 +300,83 @@ class SlabPipeline(MapPipeline):
     def _new_volumes(self):
         org, ext = self.box
         return ops.StitchedVolumes(self.cube_shape, self.device, org=org, ext=ext)
+
+
+class BalancedCubePipeline(MapPipeline):
+    """One map, its cubes dealt out EVENLY over the ranks (BASELINE configs[4]: the model-bound inference
+    loop, where whole cube layers per rank would leave 11 layers / 8 GPUs = 69 % balance).
+
+    Every rank runs the cheap pre-phase on the whole map (resample, normalise, atom bins: ~2 ms against
+    seconds of convolutions -- replicating it needs no exchange at all), cuts and feeds only ITS cubes
+    (a contiguous range of the loop order), and stores every core straight into the volume block of the
+    rank that owns that x range: local memory or a peer's over NVLink (``ops.postproc_stitch_peer`` --
+    softmax/argmax + stitch fused with its exchange, no NCCL call).  The output is thus partitioned
+    along cube axis 0, ``x_bounds[r] .. x_bounds[r+1]`` on rank r; ``finish_map()`` (stream sync +
+    barrier) makes every rank's block final.  No reference counterpart (the reference is single-GPU)."""
+
+    def __init__(self, device, rank, world, grid_size=48, padding=8, order=3, batch_cubes=16,
+                 target_voxel_size=1.0, group=None, af3_mode='sparse', cube_subset=None, _peer_volumes=None):
+        super().__init__(device, grid_size, padding, order, batch_cubes, target_voxel_size, af3_mode)
+        self.rank, self.world, self.group = int(rank), int(world), group
+        self.cube_subset = cube_subset            # optional indices into the loop-order cube list (bounded runs)
+        self.peer_volumes = _peer_volumes
+        self.x_bounds = None
+
+    def cube_index(self):
+        perm, offset = self.header.transpose_order()
+        self.perm, self.offset = perm, offset
+        self.cube_shape = ops.cube_space_shape(self.normalized.shape, perm)
+        ijk = ops.cube_origins(self.cube_shape, self.grid_size)
+        if self.cube_subset is not None:
+            ijk = ijk[np.asarray(self.cube_subset, dtype=np.int64)]
+        b = _split_even(len(ijk), self.world)
+        self.cube_range = (b[self.rank], b[self.rank + 1])
+        self.cubes_per_rank = [b[r + 1] - b[r] for r in range(self.world)]
+        self._set_cube_origins(ijk[b[self.rank]:b[self.rank + 1]],
+                               (self.cube_shape, self.grid_size, self.rank, self.world, len(ijk),
+                                None if self.cube_subset is None else hash(tuple(self.cube_subset))))
+        self.x_bounds = _split_even(self.cube_shape[0], self.world)
+        self.box = ((self.x_bounds[self.rank], 0, 0),
+                    (self.x_bounds[self.rank + 1] - self.x_bounds[self.rank], self.cube_shape[1], self.cube_shape[2]))
+        return self.ijk_host
+
+    def _new_volumes(self):
+        from .peer import PeerVolumes
+        X, Y, Z = self.cube_shape
+        n_max = max(self.x_bounds[r + 1] - self.x_bounds[r] for r in range(self.world)) * Y * Z
+        if self.peer_volumes is None or self.peer_volumes.n_voxels < n_max:
+            if self.peer_volumes is not None:
+                self.peer_volumes.close()
+            if self.world == 1:                   # nothing to map: one local block
+                self.peer_volumes = PeerVolumes.emulate(self.device, 1, n_max)[0]
+            elif self.group is False:
+                raise MicaError('in-process emulation of several ranks: pass _peer_volumes (PeerVolumes.emulate)')
+            else:
+                self.peer_volumes = PeerVolumes(self.device, self.rank, self.world, n_max, self.group)
+        org, ext = self.box
+        n = ext[0] * ext[1] * ext[2]
+        vols = ops.StitchedVolumes.from_block(self.peer_volumes.block(n_elems=23 * n), self.cube_shape, org, ext)
+        vols.block.zero_()
+        return vols
+
+    def stitch_fn(self, bb, ca, aa, ijk, vols):
+        ops.postproc_stitch_peer(bb, ca, aa, ijk, self.cube_shape, self.peer_volumes.table, self.x_bounds,
+                                 self.grid_size, self.padding)
+
+    def predict_and_stitch(self, model_fn, vols=None, on_batch=None, **kw):
+        if vols is None:
+            self.cube_index()
+            vols = self._new_volumes()
+            self.sync_ranks()                     # nobody stores into a block before its owner has cleared it
+        kw.setdefault('stitch_fn', self.stitch_fn)
+        return super().predict_and_stitch(model_fn, vols, on_batch, **kw)
+
+    def sync_ranks(self):
+        torch.cuda.synchronize(self.device)
+        if self.world > 1 and self.group is not False:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+
+    def finish_map(self):
+        """All ranks' cores have landed: after this every rank may read its own volume block."""
+        self.sync_ranks()

@@ -184,3 +184,53 @@ def synthetic_predictions(shape_xyz, n_residues=(60, 25), seed=2022, spurious=2,
     aa_pred = aa.argmax(axis=0).astype(np.float32)
     return dict(carbon_alpha_probability=ca, backbone_probability=bb,
                 amino_acid_probability=aa.astype(np.float32), amino_acid_prediction=aa_pred)
+
+
+def synthetic_map_device(shape_zyx, device, voxel=1.06, resolution=3.7, seed=2022, noise=0.05):
+    """``synthetic_map`` built on the GPU with torch ops (bench inputs of 512^3 .. 720^3: the NumPy
+    version takes half a minute there).  Same recipe -- point masses in a central blob, separable
+    Gaussian blur of sigma = 0.225 * resolution / voxel, N(0, noise) -- but a different random stream,
+    so it is NOT voxel-identical to ``synthetic_map``; every rank of a multi-GPU run that uses the
+    same seed gets the same map.  Input synthesis only: no part of the measured path."""
+    import torch
+    import torch.nn.functional as F
+    dev = torch.device(device)
+    gen = torch.Generator(device=dev).manual_seed(int(seed))
+    shape = tuple(int(s) for s in shape_zyx)
+    nvox = shape[0] * shape[1] * shape[2]
+    n_atoms = max(16, nvox // 400)
+    dims = torch.tensor(shape, dtype=torch.float32, device=dev)
+    pts = torch.randn((n_atoms, 3), generator=gen, device=dev) * (dims / 6.0) + dims / 2.0
+    pts = torch.minimum(torch.clamp(torch.round(pts), min=0), dims - 1).long()
+    lin = (pts[:, 0] * shape[1] + pts[:, 1]) * shape[2] + pts[:, 2]
+    vol = torch.zeros(nvox, dtype=torch.float32, device=dev)
+    vol.index_add_(0, lin, torch.ones(n_atoms, dtype=torch.float32, device=dev))
+    vol = vol.view(1, 1, *shape)
+    sigma = 0.225 * resolution / voxel
+    r = max(1, int(4.0 * sigma + 0.5))
+    t = torch.arange(-r, r + 1, dtype=torch.float32, device=dev)
+    k = torch.exp(-0.5 * (t / sigma) ** 2)
+    k = k / k.sum()
+    for axis in range(3):
+        ks = [1, 1, 1]
+        ks[axis] = 2 * r + 1
+        pad = [0, 0, 0]
+        pad[axis] = r
+        vol = F.conv3d(vol, k.view(1, 1, *ks), padding=tuple(pad))
+    vol = vol.view(shape)
+    vol /= vol.max().clamp_min(1e-12)
+    vol += torch.randn(shape, generator=gen, device=dev) * noise
+    return vol.contiguous()
+
+
+def pointwise_model(x, af):
+    """Deterministic elementwise stand-in for ``MICA.forward(exp_map, af_features) -> (bb, ca, aa)``:
+    the logits of a voxel depend only on that voxel's inputs, so two runs that cut the same cube get the
+    same logits whatever the batching, the rank or the call order (parity legs of bench.py / tests)."""
+    import math
+    import torch
+    s = af.sum(dim=1, keepdim=True)
+    bb = torch.cat([x, -x, 2 * x - 0.5 + s, x * x], dim=1)
+    ca = torch.cat([0.5 - x, x, x * 3 - 1, 1.5 * x + af[:, :1]], dim=1)
+    aa = torch.cat([x * (0.1 * t) + af[:, t % 24:t % 24 + 1] * (t % 3) + math.sin(t) for t in range(21)], dim=1)
+    return bb, ca, aa

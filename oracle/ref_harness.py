@@ -20,12 +20,31 @@ import sys
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get('MICA_REFERENCE_ROOT', '/root/reference')
-_STANDINS = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'standins')
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STANDINS = os.path.join(_HERE, 'standins')
+#: the staged archive of the unmodified reference (oracle/make_ref.py; travels to the GPU box)
+STAGED_ARCHIVE = os.path.join(_HERE, '_ref', 'reference_py.zip')
+
+
+def _find_root():
+    root = os.environ.get('MICA_REFERENCE_ROOT', '/root/reference')
+    if os.path.isfile(os.path.join(root, 'utils', 'preprocessing.py')):
+        return root
+    if os.path.isfile(STAGED_ARCHIVE):
+        return STAGED_ARCHIVE                       # imported through zipimport
+    return root
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, 'utils', 'preprocessing.py'))
+    return REFERENCE_ROOT == STAGED_ARCHIVE or os.path.isfile(os.path.join(REFERENCE_ROOT, 'utils', 'preprocessing.py'))
+
+
+def live_tree() -> bool:
+    """True when the reference's source tree itself is present (the build container)."""
+    return REFERENCE_ROOT != STAGED_ARCHIVE and available()
 
 
 def _setup_path():
@@ -41,7 +60,7 @@ def _setup_path():
 
 @contextlib.contextmanager
 def _quiet():
-    with contextlib.redirect_stdout(io.StringIO()):
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
         yield
 
 

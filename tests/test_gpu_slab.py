@@ -133,3 +133,105 @@ def test_peer_memory_histogram_exchange_equals_single_gpu(cuda, world):
             assert got[3] == 0, f'rank {r}: status {got[3]}'
             assert got[:3] == want[:3], (r, got, want)
     groups[0].close()
+
+
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_peer_memory_halo_exchange_assembles_the_source_planes(cuda, world):
+    """mica_halo_publish / mica_halo_pull with `world` emulated ranks (own streams, plain pointers instead of
+    IPC): every rank's assembled buffer must equal its planes [src_lo, src_hi) of the whole map, over
+    several epochs (slot parity) and with maps that change from epoch to epoch."""
+    from mica_b200.peer import PeerHalo
+    src_shape, voxel, gs, pad = (96 * world, 24, 20), 1.1, 32, 16
+    plan = SlabPlan(src_shape, (np.float32(voxel),) * 3, gs, pad, world)
+    plane = src_shape[1] * src_shape[2]
+    need = 0
+    for r in range(world):
+        np_ = PeerHalo.neighbour_plan(plan, r)
+        assert np_ is not None
+        need = max([need] + [b - a for rng in np_ if rng is not None for a, b in [rng]])
+    groups = PeerHalo.emulate(cuda, world, need * plane)
+    assert all(g.fits(plan, g.rank) for g in groups)
+    streams = [torch.cuda.Stream(cuda) for _ in range(world)]
+    g = torch.Generator(device=cuda).manual_seed(3)
+    for epoch in range(3):
+        full = torch.rand(src_shape, generator=g, device=cuda)
+        torch.cuda.synchronize()
+        owns, bufs = [], []
+        for r in range(world):                            # publish never waits: issue all of them first
+            me = plan.ranks[r]
+            own = full[me.own_lo:me.own_hi].contiguous()
+            owns.append(own)
+            with torch.cuda.stream(streams[r]):
+                groups[r].publish(own, plan, streams[r].cuda_stream)
+        for r in range(world):
+            me = plan.ranks[r]
+            with torch.cuda.stream(streams[r]):
+                buf = torch.full((me.src_hi - me.src_lo,) + src_shape[1:], -1.0, device=cuda)
+                lo, hi = max(me.src_lo, me.own_lo), min(me.src_hi, me.own_hi)
+                buf[lo - me.src_lo:hi - me.src_lo].copy_(owns[r][lo - me.own_lo:hi - me.own_lo])
+                groups[r].pull(buf, plan, streams[r].cuda_stream)
+            bufs.append(buf)
+        torch.cuda.synchronize()
+        for r in range(world):
+            me = plan.ranks[r]
+            assert not groups[r].timed_out()
+            assert torch.equal(bufs[r], full[me.src_lo:me.src_hi]), (epoch, r)
+    groups[0].close()
+
+
+def test_peer_halo_times_out_instead_of_hanging(cuda):
+    """A neighbour that never publishes turns into a status word after the bounded spin."""
+    from mica_b200.peer import PeerHalo
+    plan = SlabPlan((80, 8, 8), (np.float32(1.1),) * 3, 32, 16, 2)
+    groups = PeerHalo.emulate(cuda, 2, 64 * 64)
+    me = plan.ranks[0]
+    buf = torch.zeros((me.src_hi - me.src_lo, 8, 8), device=cuda)
+    groups[0].epoch = 1                                   # rank 1 never published epoch 1
+    import time
+    t0 = time.time()
+    groups[0].pull(buf, plan)
+    torch.cuda.synchronize()
+    assert groups[0].timed_out() and time.time() - t0 < 20
+    groups[0].close()
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_balanced_cube_ranks_store_cores_into_the_owners_volumes(cuda, world):
+    """config 5 dataflow, emulated: the cubes of ONE map dealt out evenly, every core stored into the volume
+    block of the rank that owns its x range (postproc_stitch_peer); the union of the blocks must be bit-equal
+    to the single-GPU volumes."""
+    from mica_b200.peer import PeerVolumes
+    from mica_b200.slab import BalancedCubePipeline
+    src = synthetic.synthetic_map((56, 40, 100), voxel=1.0, seed=21)
+    hdr = MapHeader(voxel_size=(np.float32(1.0),) * 3)
+    d_src = torch.from_numpy(src).to(cuda)
+    st = synthetic.synthetic_structure(200, (100, 40, 56), seed=21)
+    bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
+    atoms = tuple(torch.from_numpy(a).to(cuda) for a in (st['coords'], bb_ch, aa_ch))
+    single = MapPipeline(cuda, 32, 16, batch_cubes=5)
+    with torch.no_grad():
+        want = single.run(d_src, hdr, atoms, synthetic.pointwise_model)
+    X, Y, Z = single.cube_shape
+    pipes = [BalancedCubePipeline(cuda, r, world, 32, 16, batch_cubes=5, group=False) for r in range(world)]
+    for p in pipes:
+        assert p.resample_and_normalize(d_src, hdr) and p.encode_af3(*atoms)
+        p.cube_index()
+    n_max = max(pipes[0].x_bounds[r + 1] - pipes[0].x_bounds[r] for r in range(world)) * Y * Z
+    groups = PeerVolumes.emulate(cuda, world, n_max)
+    vols = []
+    for p, g_ in zip(pipes, groups):                       # every owner clears its block BEFORE anybody stores
+        p.peer_volumes = g_
+        vols.append(p._new_volumes())
+    assert sum(len(p.ijk_host) for p in pipes) == len(single.ijk_host)
+    assert max(p.cubes_per_rank) - min(p.cubes_per_rank) <= 1
+    with torch.no_grad():
+        for p, v in zip(pipes, vols):
+            p.predict_and_stitch(synthetic.pointwise_model, v, model_batch=2, d8='split')
+    torch.cuda.synchronize()
+    for r, (p, v) in enumerate(zip(pipes, vols)):
+        x0, x1 = p.x_bounds[r], p.x_bounds[r + 1]
+        for k, t in v.as_dict().items():
+            ref = want.as_dict()[k]
+            ref = ref[:, x0:x1] if ref.dim() == 4 else ref[x0:x1]
+            assert torch.equal(t, ref), (r, k)
+    groups[0].close()
