@@ -98,6 +98,15 @@ int mica_bspline_resample_f32(const float* src, int sz, int sy, int sx, int src_
  * branches on results.
  */
 size_t mica_select_workspace_bytes(void);
+/* With room for the COMPACT BUFFER: the guided digit-0 pass appends every voxel of the candidate bins (a few
+ * percent of the map) to it, and the four later digit passes read that buffer instead of streaming the map
+ * again (order statistics: 6 map reads -> 2).  mica_select_workspace_bytes_for(n) sizes a workspace for n
+ * voxels per rank; after allocating (and zero-filling) it call mica_select_set_compact once.  A workspace
+ * of the plain size, or an overflowing buffer (heavy ties), falls back to streaming the map: same results. */
+size_t mica_select_workspace_bytes_for(int64_t n_local);
+int mica_select_set_compact(void* workspace, size_t workspace_bytes, mica_stream_t stream);
+/* diagnostics: out = {compact buffer in use (0|1), floats appended, capacity}; synchronises the stream */
+int mica_select_compact_info(const void* workspace, int64_t out[3], mica_stream_t stream);
 int mica_select_init(void* workspace, int64_t n_total, mica_stream_t stream);
 int mica_select_hist(const float* x, int64_t n_local, void* workspace, int step, mica_stream_t stream);
 int64_t* mica_select_hist_ptr(void* workspace);

@@ -44,6 +44,9 @@ SIGNATURES = {
     'mica_resample_force_generic': (_i, [_i]),
     'mica_bspline_resample_f32': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     'mica_select_workspace_bytes': (_sz, []),
+    'mica_select_workspace_bytes_for': (_sz, [_i64]),
+    'mica_select_set_compact': (_i, [_p, _sz, _p]),
+    'mica_select_compact_info': (_i, [_p, C.POINTER(_i64), _p]),
     'mica_select_init': (_i, [_p, _i64, _p]),
     'mica_select_hist': (_i, [_p, _i64, _p, _i, _p]),
     'mica_select_hist_ptr': (_p, [_p]),

@@ -39,6 +39,8 @@ def _scalar_i64(t: torch.Tensor) -> int:
 
 
 def _as_device(v, device):
+    if hasattr(v, 'tensor') and isinstance(getattr(v, 'tensor'), torch.Tensor):
+        v = v.tensor                         # predict.DeviceVolume: the volume never left HBM
     if isinstance(v, torch.Tensor):
         if not v.is_cuda:
             ops.require_gpu()
@@ -140,6 +142,7 @@ def find_candidates(volumes, CA_score_thrh=0.3, cluster_eps=10, cluster_min_poin
         volumes = volumes.as_dict()
     dev = torch.device(device)
     for v in volumes.values():
+        v = getattr(v, 'tensor', v)
         if isinstance(v, torch.Tensor) and v.is_cuda:
             dev = v.device
             break

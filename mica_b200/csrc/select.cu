@@ -40,8 +40,18 @@ struct SelectState {
   float g;                    // percentile interpolation weight
   int phase0;                 // digit 0: 0 = sample pending, 1 = guided pass pending, 2 = full pass pending, 3 = done
   int cand[3];                // candidate digit-0 bins from the sample: median in [cand0, cand1], percentile >= cand2
-  int pad2;
+  int comp_ok;                // 1 = the compact buffer holds every voxel of the candidate bins (digits 1, 2 read it)
+  // compact buffer (follows the state in the workspace): the voxels the guided pass found in the candidate
+  // bins -- a few percent of the map -- so that the four later digit passes do not stream the map again
+  long long comp_cap;         // capacity in floats; set once per workspace (mica_select_set_compact), survives init
+  unsigned long long comp_count;   // floats appended by the guided pass (> comp_cap = overflow: not usable)
 };
+
+constexpr int kCompStage = 160;   // per-warp staging slots of the guided pass (flushed when < 32 are free)
+
+__host__ __device__ __forceinline__ float* comp_buffer(SelectState* s) {
+  return reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s + 1) + 255) / 256 * 256);
+}
 
 static_assert(sizeof(long long) * 2 * kBins == MICA_SELECT_HIST_WORDS * 8, "hist words");
 
@@ -109,6 +119,11 @@ select_hist_kernel(const float* __restrict__ x, long long n, SelectState* __rest
   __shared__ unsigned h[2 * kBins];
   const int round = s->round;
   if (round == 0 || round >= kDigitRounds || s->phase0 != 3 || s->status != MICA_NORM_PENDING) return;   // digit 0 has its own kernels
+  if (s->comp_ok) {   // every voxel these digits can count was compacted by the guided pass
+    x = comp_buffer(s);
+    n = (long long)s->comp_count;
+    if ((long long)blockIdx.x * blockDim.x * 4 >= n) return;   // the grid is sized for the whole map
+  }
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) h[i] = 0;
   __syncthreads();
   const int digit = round_digit(round);
@@ -271,10 +286,34 @@ __global__ void __launch_bounds__(512)
 select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
   __shared__ unsigned h[kBins];
   __shared__ unsigned long long lump[2];
+  __shared__ float stage_all[16][kCompStage];
   if (s->phase0 != 1 || s->status != MICA_NORM_PENDING) return;
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
   if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
   __syncthreads();
+  // candidate voxels are appended to the compact buffer: staged per warp (ballot-ranked, no atomics), one
+  // global atomic per ~130 candidates reserves the run, the warp writes it coalesced
+  float* const comp = comp_buffer(s);
+  const long long comp_cap = s->comp_cap;
+  float* const stage = stage_all[threadIdx.x >> 5];
+  const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+  int staged = 0;   // warp-uniform
+  auto flush = [&]() {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&s->comp_count, (unsigned long long)staged);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    if ((long long)(base + staged) <= comp_cap)
+      for (int i = lane; i < staged; i += 32) comp[base + i] = stage[i];
+    __syncwarp();
+    staged = 0;
+  };
+  auto append = [&](unsigned m, bool mine, float v) {   // m = ballot of `mine` over the (converged) warp
+    if (comp_cap == 0) return;
+    if (mine) stage[staged + __popc(m & lt_mask)] = v;
+    staged += __popc(m);
+    if (staged > kCompStage - 32) flush();
+  };
   const unsigned a_lo = (unsigned)s->cand[0], a_w = (unsigned)(s->cand[1] - s->cand[0]), p_lo = (unsigned)s->cand[2];
   unsigned c0 = 0, c1 = 0;   // voxels below A_lo / between A_hi and P_lo seen by this thread
   auto classify = [&](float v, unsigned& bin) -> bool {
@@ -291,9 +330,20 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   unsigned bin;
-  if (tid < head && classify(x[tid], bin)) atomicAdd(&h[bin], 1u);
-  for (long long i = head + n4 * 4 + tid; i < n; i += stride)
-    if (classify(x[i], bin)) atomicAdd(&h[bin], 1u);
+  // head (< 4 scalars) and tail (< 4 scalars): only the first lanes of block 0's first warp see them; the
+  // whole warp walks through the append so that the ballots stay converged
+  {
+    const long long n_edge = head + (n - head - n4 * 4);   // <= 6
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+      const long long e = threadIdx.x;
+      const bool have = e < n_edge;
+      const long long idx = e < head ? e : head + n4 * 4 + (e - head);
+      const float v = have ? x[idx] : 0.f;
+      const bool exact = have && classify(v, bin);
+      if (exact) atomicAdd(&h[bin], 1u);
+      append(__ballot_sync(0xffffffffu, exact), exact, v);
+    }
+  }
   const long long n4_pad = (n4 + 31) & ~31LL;
   for (long long i = tid; i < n4_pad; i += stride) {
     const bool ok = i < n4;
@@ -304,6 +354,7 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
       const bool exact = ok && classify(vv[c], bin);
       const unsigned m = __ballot_sync(0xffffffffu, exact);
       if (m == 0u) continue;
+      append(m, exact, vv[c]);
       if (__popc(m) <= 8) {            // a few candidates: plain shared atomics
         if (exact) atomicAdd(&h[bin], 1u);
       } else if (exact) {              // many (ties, masked maps): one atomic per distinct bin
@@ -312,6 +363,7 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
       }
     }
   }
+  if (staged > 0) flush();
   // block totals of the two counters
   for (int o = 16; o > 0; o >>= 1) {
     c0 += __shfl_xor_sync(0xffffffffu, c0, o);
@@ -479,6 +531,9 @@ select_pick_kernel(SelectState* s, int t) {
         verdict = 0;
         s->phase0 = 2;      // run the full histogram (host step 2)
       }
+      // the compact buffer is usable when the guided pass was accepted and nothing overflowed; in a
+      // multi-GPU run every rank decides for its own buffer (the reduced histograms do not depend on it)
+      s->comp_ok = (med_ok && tail_ok && s->comp_cap > 0 && s->comp_count <= (unsigned long long)s->comp_cap) ? 1 : 0;
     }
     __syncthreads();
     if (!verdict) {
@@ -679,6 +734,8 @@ __global__ void select_init_kernel(SelectState* s, long long n_total) {
     s->cand[0] = 0;
     s->cand[1] = kBins - 1;
     s->cand[2] = 0;
+    s->comp_ok = 0;
+    s->comp_count = 0ull;
     s->status = n_total > 0 ? MICA_NORM_PENDING : MICA_NORM_NO_POSITIVE;
     s->n_le_med = 0;
     s->n_pos = 0;
@@ -750,6 +807,34 @@ normalize_apply_kernel(const float* __restrict__ x, float* __restrict__ y, long 
 using namespace mica;
 
 extern "C" size_t mica_select_workspace_bytes(void) { return sizeof(SelectState) + 256; }
+
+// capacity of the compact buffer for n_local voxels per rank: the candidate bins hold ~4 % of a density map
+// (sample quantiles 0.48-0.52 and the top 0.3 %) plus whatever shares their digit-0 bins; 1/8 of the map
+// leaves room for coarse bins, and an overflow only means the digit passes stream the map as before
+static long long compact_capacity(int64_t n_local) {
+  if (n_local < (1 << 22)) return 0;              // small inputs: the full passes cost microseconds
+  return (long long)(n_local / 8 + 4095) / 4096 * 4096;
+}
+
+extern "C" size_t mica_select_workspace_bytes_for(int64_t n_local) {
+  return mica_select_workspace_bytes() + 256 + (size_t)compact_capacity(n_local) * sizeof(float);
+}
+
+__global__ void select_set_compact_kernel(SelectState* s, long long cap) { s->comp_cap = cap; }
+
+// Tell a (zero-initialised) workspace how large it is: everything beyond the state becomes the compact
+// buffer.  Once per allocation; mica_select_init keeps the setting.
+extern "C" int mica_select_set_compact(void* workspace, size_t workspace_bytes, mica_stream_t stream) {
+  MICA_REQUIRE(workspace, "null workspace");
+  MICA_REQUIRE(workspace_bytes >= mica_select_workspace_bytes(), "workspace smaller than the select state");
+  SelectState* s = (SelectState*)(((uintptr_t)workspace + 255) / 256 * 256);
+  const uintptr_t end = (uintptr_t)workspace + workspace_bytes;
+  const uintptr_t buf = (uintptr_t)comp_buffer(s);
+  const long long cap = end > buf ? (long long)((end - buf) / sizeof(float)) : 0;
+  select_set_compact_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(s, cap);
+  MICA_LAUNCH_CHECK("select_set_compact_kernel");
+  return MICA_OK;
+}
 
 static SelectState* state_of(const void* ws) { return (SelectState*)(((uintptr_t)ws + 255) / 256 * 256); }
 
@@ -914,6 +999,24 @@ extern "C" int mica_select_result(const void* workspace, float* median, float* p
   if (p999) *p999 = r.p;
   if (n_pos) *n_pos = r.n_pos;
   if (norm_status) *norm_status = r.status;
+  return MICA_OK;
+}
+
+// test / diagnostics hook: {comp_ok, comp_count, comp_cap} of a workspace (synchronises the stream)
+extern "C" int mica_select_compact_info(const void* workspace, int64_t out[3], mica_stream_t stream) {
+  MICA_REQUIRE(workspace && out, "null pointer");
+  const SelectState* s = state_of(workspace);
+  int ok = 0;
+  long long cap = 0;
+  unsigned long long cnt = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  MICA_CUDA(cudaMemcpyAsync(&ok, &s->comp_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaMemcpyAsync(&cap, &s->comp_cap, sizeof(cap), cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaMemcpyAsync(&cnt, &s->comp_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+  MICA_CUDA(cudaStreamSynchronize(st));
+  out[0] = ok;
+  out[1] = (int64_t)cnt;
+  out[2] = cap;
   return MICA_OK;
 }
 

@@ -113,10 +113,24 @@ def resample(src: torch.Tensor, out_shape, order: int = 3, *, src_z0: int = 0, s
 class OrderStats:
     """Device-resident state of the exact radix select (median + 99.9 percentile)."""
 
-    def __init__(self, device):
+    def __init__(self, device, n_hint: int = 0):
+        """``n_hint``: voxels per rank the workspace should hold a compact buffer for (0 = allocate it on the
+        first ``run``).  The guided digit-0 pass compacts the candidate voxels there and the later digit passes
+        read them instead of streaming the map four more times; without room they stream the map."""
         self.device = torch.device(device)
-        self.ws = torch.zeros(lib.mica_select_workspace_bytes(), dtype=torch.uint8, device=device)
-        self._p = C.c_void_p(self.ws.data_ptr())
+        if self.device.type != 'cuda':
+            raise _lib.MicaError(f'OrderStats needs a CUDA device, got {self.device} (mica_b200 has no CPU fallback)')
+        self._n_cap = -1
+        self._alloc(int(n_hint))
+
+    def _alloc(self, n_local: int):
+        with torch.cuda.device(self.device):
+            nbytes = lib.mica_select_workspace_bytes_for(n_local) if n_local > 0 else lib.mica_select_workspace_bytes()
+            self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+            self._p = C.c_void_p(self.ws.data_ptr())
+            if n_local > 0:
+                check(lib.mica_select_set_compact(self._p, nbytes, _stream()), 'select_set_compact')
+            self._n_cap = n_local
 
     def hist_view(self) -> torch.Tensor:
         """int64 view of the histogram words a multi-GPU run all-reduces between hist and pick."""
@@ -132,6 +146,8 @@ class OrderStats:
         p_x = _dev(x, torch.float32, 'x')
         n_local = x.numel()
         n_total = n_local if n_total is None else int(n_total)
+        if n_local > self._n_cap and n_local >= (1 << 22):     # first map, or a larger one: (re)size the compact buffer
+            self._alloc(n_local)
         st = _stream()
         if all_reduce is None and peer is None:
             check(lib.mica_order_stats_f32(p_x, n_local, self._p, st), 'order_stats')
@@ -148,6 +164,13 @@ class OrderStats:
         return self
 
     @device_guard
+    def compact_info(self):
+        """(in_use, floats_appended, capacity) of the compact buffer after a run -- synchronises the stream."""
+        out = (C.c_int64 * 3)()
+        with torch.cuda.device(self.device):
+            check(lib.mica_select_compact_info(self._p, out, _stream()), 'select_compact_info')
+        return bool(out[0]), int(out[1]), int(out[2])
+
     def result(self):
         """(median, p999, n_pos, status) -- synchronises the stream."""
         med, p, npos, status = C.c_float(), C.c_float(), C.c_int64(), C.c_int()

@@ -61,8 +61,11 @@ def _fixed3(txt8):
         return None
     if (minus[1:4] & (t[0:3] != 32)).any():               # and only blanks before the sign
         return None
-    d = np.where(dig, t - 48, 0).astype(np.int32)
-    n = (((((d[0] * 10 + d[1]) * 10 + d[2]) * 10 + d[3]) * 10 + d[5]) * 10 + d[6]) * 10 + d[7]
+    d = (t - 48) * dig                                    # uint8 digit values, 0 where blank / sign
+    n = d[0].astype(np.int32)
+    for j in (1, 2, 3, 5, 6, 7):
+        n *= 10
+        n += d[j]
     val = n.astype(np.float64) / 1000.0
     return np.where(minus.any(axis=0), -val, val)
 
@@ -70,15 +73,17 @@ def _fixed3(txt8):
 def _records(path, with_hetatm):
     """Column-wise parse of the ATOM (and HETATM) records.  Returns a dict of per-record arrays in file
     order after the Bio.PDB de-duplication: cols (uint8 [A,60]), is_het, model, coords float32 [A,3]."""
-    raw = np.fromfile(path, dtype=np.uint8)
-    if raw.size == 0:
+    with open(path, 'rb') as fh:
+        data = fh.read()
+    if not data:
         return None
-    first_nl = np.flatnonzero(raw[:4096] == 10)
-    L = int(first_nl[0]) + 1 if len(first_nl) else 0
+    raw = np.frombuffer(data, dtype=np.uint8)
+    L = data.find(b'\n') + 1
     n_full = raw.size // L if L else 0
     tail = raw[n_full * L:] if L else raw
     fixed = (L >= _COLS + 1 and n_full > 0 and bool((raw[L - 1:n_full * L:L] == 10).all())
-             and int(np.count_nonzero(raw == 10)) == n_full + int(tail.size > 0 and tail[-1] == 10))
+             and data.count(b'\n') == n_full + int(tail.size > 0 and tail[-1] == 10))
+    has_cr = data.find(b'\r') >= 0
     if fixed:
         # every line has the same length (what PDB writers produce): the file IS the column table
         table = raw[:n_full * L].reshape(n_full, L)
@@ -114,7 +119,8 @@ def _records(path, with_hetatm):
         inside = idx < e[:, None]
         cols = np.where(inside, raw[np.minimum(idx, raw.size - 1)], 32).astype(np.uint8)
         het = is_het[sel]
-    cols[cols == 13] = 32                                # CR of CRLF files
+    if has_cr:
+        cols[cols == 13] = 32                            # CR of CRLF files
     if len(cols):
         txt = np.ascontiguousarray(cols[:, 30:54]).reshape(-1, 8)      # x, y, z fields of every record
         v = _fixed3(txt)

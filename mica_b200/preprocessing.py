@@ -20,6 +20,39 @@ from . import mrc, ops, pdb, session
 from .pipeline import MapHeader, shared_pipeline
 
 
+_STAGING = {}
+
+
+def upload_map(data: np.ndarray, device) -> torch.Tensor:
+    """Host map (typically the copy-on-write memory map ``mrc.read_mrc`` returns) -> device tensor: the
+    planes are copied into a reused pinned staging buffer by a few threads (NumPy releases the GIL) and
+    every finished chunk goes to the GPU at once, instead of one pageable copy of the whole map."""
+    from concurrent.futures import ThreadPoolExecutor
+    data = np.asarray(data)
+    dev = torch.device(device)
+    n = data.size
+    out = torch.empty(data.shape, dtype=torch.float32, device=dev)
+    if n < (1 << 22) or data.dtype != np.float32 or not data.flags.c_contiguous:
+        out.copy_(torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)))
+        return out
+    stage = _STAGING.get('map')
+    if stage is None or stage.numel() < n:
+        stage = _STAGING['map'] = torch.empty(n, dtype=torch.float32).pin_memory()
+    flat_src, flat_dst, flat_out = data.reshape(-1), stage.numpy(), out.view(-1)
+    chunks = 8
+    bounds = [n * c // chunks for c in range(chunks + 1)]
+    with torch.cuda.device(dev):
+        torch.cuda.current_stream().synchronize()        # the staging buffer may still feed the previous map
+
+        def fill(c):
+            flat_dst[bounds[c]:bounds[c + 1]] = flat_src[bounds[c]:bounds[c + 1]]
+            return c
+        with ThreadPoolExecutor(4) as pool:
+            for c in pool.map(fill, range(chunks)):
+                flat_out[bounds[c]:bounds[c + 1]].copy_(stage[bounds[c]:bounds[c + 1]], non_blocking=True)
+    return out
+
+
 def _header_of(m, voxel_size=None):
     return MapHeader(voxel_size=m.voxel_size if voxel_size is None else voxel_size, origin=m.origin,
                      mapc=m.mapc, mapr=m.mapr, maps=m.maps, nxstart=m.nxstart, nystart=m.nystart,
@@ -75,7 +108,7 @@ class DataPreprocessor:
                 raise ValueError(f'MRC mode {m.mode} maps are not supported (float32 / mode 2 only)')
             header = _header_of(m)
             pipe = shared_pipeline(self.device).configure(order=self.order, target_voxel_size=target_voxel_size)
-            src = torch.from_numpy(np.asarray(m.data)).to(pipe.device)
+            src = upload_map(m.data, pipe.device)
             if pipe.resample_and_normalize(src, header):
                 out_path = os.path.join(os.path.dirname(self.AF3_results), 'resampled_normalized_map.mrc')
                 out_header = _header_of(m, voxel_size=(np.float32(target_voxel_size),) * 3)

@@ -20,6 +20,7 @@ import os
 import time
 
 _REGISTRY: dict[str, dict] = {}
+_META: dict[str, tuple] = {}          # key -> (time of registration, mtime of the file then or None)
 
 
 def _key(path) -> str:
@@ -35,8 +36,7 @@ def _mtime(key):
 
 def put(path, **entry):
     key = _key(path)
-    entry['_registered'] = time.time()
-    entry['_mtime'] = _mtime(key)
+    _META[key] = (time.time(), _mtime(key))
     _REGISTRY[key] = entry
     return entry
 
@@ -48,25 +48,27 @@ def get(path):
         return None
     now = _mtime(key)
     if now is not None and os.path.isfile(key):
-        seen = entry.get('_mtime')
+        registered, seen = _META.get(key, (0.0, None))
         # a file that appeared or changed after registration (1 s slack for coarse clocks and for the
         # drop-in's own write_files=True output, written just before the entry is registered)
-        if (seen is None and now > entry['_registered'] + 1.0) or (seen is not None and now > seen + 1e-6):
-            _REGISTRY.pop(key, None)
+        if (seen is None and now > registered + 1.0) or (seen is not None and now > seen + 1e-6):
+            drop(key)
             return None
     return entry
 
 
 def drop(path):
     _REGISTRY.pop(_key(path), None)
+    _META.pop(_key(path), None)
 
 
 def release_under(path):
     """Drop every entry at or below ``path`` (e.g. a map's working directory)."""
     root = _key(path)
     for k in [k for k in _REGISTRY if k == root or k.startswith(root + os.sep)]:
-        _REGISTRY.pop(k, None)
+        drop(k)
 
 
 def clear():
     _REGISTRY.clear()
+    _META.clear()

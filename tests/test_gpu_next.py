@@ -331,7 +331,11 @@ def test_predictor_keeps_volumes_resident_for_the_clustering_head(cuda, tmp_path
     assert pr.select_processing_strategy()
     pr.model = Replay(pr._source['ijk'], 64, 8)
     ok, host = pr.run_prediction()
-    assert ok and set(host) == {'backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction'}
+    assert ok and set(host) == {'backbone_probability', 'carbon_alpha_probability', 'amino_acid_prediction',
+                                'amino_acid_probability'}
+    from mica_b200.predict import DeviceVolume                      # the 20-channel volume stays in HBM
+    assert isinstance(host['amino_acid_probability'], DeviceVolume) and host['amino_acid_probability'].tensor.is_cuda
+    assert all(isinstance(host[k], np.ndarray) for k in host if k != 'amino_acid_probability')
     reg = session.get(os.path.join(out_path, 'results', 'device_volumes'))
     assert reg is not None and reg['amino_acid_probability'].is_cuda and tuple(reg['amino_acid_probability'].shape) == (20, X, Y, Z)
     full = {k: v.cpu().numpy() for k, v in reg.items()}

@@ -204,6 +204,52 @@ def test_order_stats_guided_pass_fallback_and_adversarial_sample(cuda):
     assert np.array_equal(norm.cpu().numpy(), want[0])
 
 
+def test_order_stats_compact_buffer_paths(cuda):
+    """From 4 M voxels on, the guided digit-0 pass compacts the candidate voxels and the four later digit
+    passes read that buffer instead of the map.  Thresholds must stay NumPy's on every path: buffer used,
+    buffer overflowing (heavy ties: the median's bin holds most of the map), guided pass rejected, an
+    unaligned array (scalar head / tail), and a second, smaller map through the same workspace."""
+    rng = np.random.default_rng(33)
+    n = 6_000_003
+    x = (rng.standard_normal(n) * 0.05).astype(np.float32)
+    x[::41] += rng.random(x[::41].shape, dtype=np.float32)
+    st = ops.OrderStats(cuda)
+
+    def check(arr, expect_used):
+        want = orc.normalize(arr)
+        d = dev(arr, cuda) if isinstance(arr, np.ndarray) else arr
+        st.run(d)
+        med, p, npos, status = st.result()
+        used, count, cap = st.compact_info()
+        assert status == 0 and np.float32(med) == np.float32(want[1]) and np.float32(p) == np.float32(want[2]), (med, p, want[1:])
+        assert np.array_equal(st.apply(d).cpu().numpy(), want[0])
+        if expect_used is not None:
+            assert used == expect_used, (used, count, cap)
+        return used, count, cap
+
+    used, count, cap = check(x, True)
+    assert 0 < count < cap and cap >= n // 8                   # a few percent of the map
+    ties = x.copy()
+    ties[: int(0.6 * n)] = 0.0125                              # the median's digit-0 bin overflows the buffer
+    rng.shuffle(ties)
+    used, count, cap = check(ties, False)
+    assert count > cap
+    was = _lib.lib.mica_select_force_fallback(1)               # guided pass rejected -> full histogram, no buffer
+    try:
+        check(x, False)
+    finally:
+        _lib.lib.mica_select_force_fallback(was)
+    big = dev(np.concatenate([np.zeros(1, np.float32), x]), cuda)
+    want = orc.normalize(x)                                    # x[1:] of a 16-byte aligned buffer: unaligned view
+    view = big[1:]
+    st.run(view)
+    med, p, _, status = st.result()
+    assert status == 0 and np.float32(med) == np.float32(want[1]) and np.float32(p) == np.float32(want[2])
+    assert st.compact_info()[0] is True
+    check(x[:4_500_001].copy(), True)                          # smaller map, same workspace
+    check(x[:100_000].copy(), None)                            # tiny map: everything is a candidate
+
+
 def test_normalize_bit_exact_on_oracle_resampled(cuda, golden_dir):
     """Stage isolation: feed SciPy's own float32 volume to the GPU normaliser."""
     g = np.load(os.path.join(golden_dir, 'preprocess_small.npz'))
