@@ -134,25 +134,31 @@ __device__ __forceinline__ void iir_line(double* line, int n, int stride) {
 constexpr double kGain = (1.0 - kPole) * (1.0 - 1.0 / kPole);  // = 6
 
 // lines along a strided axis.  grid = (ceil(n_cols / CW), n_outer)
-template <typename TIn, int CW>
+// Strides of a column pass: sample k of column j of outer index o sits at
+//   in [o * outer_in  + k * line_in  + j]     out[o * outer_out + k * line_out + j]
+// (in and out differ when the output volume has a padded row pitch or another element type).
+struct ColStrides {
+  int64_t line_in, line_out, outer_in, outer_out;
+};
+
+template <typename TIn, typename TOut, int CW>
 __global__ void __launch_bounds__(256)
-prefilter_cols(const TIn* __restrict__ in, double* __restrict__ out, int n, int64_t line_stride,
-               int n_cols, int64_t outer_stride) {
+prefilter_cols(const TIn* __restrict__ in, TOut* __restrict__ out, int n, int n_cols, ColStrides S) {
   extern __shared__ double tile[];  // [n][CW]
   const int col0 = blockIdx.x * CW;
-  const int64_t base = (int64_t)blockIdx.y * outer_stride + col0;
+  const int64_t base_in = (int64_t)blockIdx.y * S.outer_in + col0, base_out = (int64_t)blockIdx.y * S.outer_out + col0;
   const int ncol = min(CW, n_cols - col0);
   const double gain = (n >= 2) ? kGain : 1.0;  // SciPy leaves length-1 axes unfiltered
   for (int e = threadIdx.x; e < n * CW; e += blockDim.x) {
     int k = e / CW, j = e % CW;
-    if (j < ncol) tile[e] = (double)in[base + (int64_t)k * line_stride + j] * gain;
+    if (j < ncol) tile[e] = (double)in[base_in + (int64_t)k * S.line_in + j] * gain;
   }
   __syncthreads();
   if (threadIdx.x < ncol) iir_line(tile + threadIdx.x, n, CW);
   __syncthreads();
   for (int e = threadIdx.x; e < n * CW; e += blockDim.x) {
     int k = e / CW, j = e % CW;
-    if (j < ncol) out[base + (int64_t)k * line_stride + j] = tile[e];
+    if (j < ncol) out[base_out + (int64_t)k * S.line_out + j] = (TOut)tile[e];
   }
 }
 
@@ -241,25 +247,30 @@ __device__ __forceinline__ void iir_segment(double* line, int n, int stride, int
 
 // lines along a strided axis.  grid = (ceil(n_cols / L), n_outer), block = 256, tile [n][L],
 // 256 / L segments per line
-template <typename TIn, int L>
+template <typename TIn, typename TOut, int L>
 __global__ void __launch_bounds__(256)
-prefilter_cols_seg(const TIn* __restrict__ in, double* __restrict__ out, int n, int64_t line_stride,
-                   int n_cols, int64_t outer_stride) {
+prefilter_cols_seg(const TIn* __restrict__ in, TOut* __restrict__ out, int n, int n_cols, ColStrides S) {
   extern __shared__ double tile[];
   constexpr int kSegs = 256 / L;
   const int col0 = blockIdx.x * L;
-  const int64_t base = (int64_t)blockIdx.y * outer_stride + col0;
+  const int64_t base_in = (int64_t)blockIdx.y * S.outer_in + col0, base_out = (int64_t)blockIdx.y * S.outer_out + col0;
   const int ncol = min(L, n_cols - col0);
   const int j = threadIdx.x & (L - 1), seg = threadIdx.x / L;
-  for (int k = seg; k < n; k += kSegs)
-    if (j < ncol) tile[k * L + j] = (double)in[base + (int64_t)k * line_stride + j] * kGain;
+  if (j < ncol) {
+    const TIn* p = in + base_in + j;
+#pragma unroll 8
+    for (int k = seg; k < n; k += kSegs) tile[k * L + j] = (double)p[(int64_t)k * S.line_in] * kGain;
+  }
   __syncthreads();
   const int len = (n + kSegs - 1) / kSegs;
   const int k0 = seg * len, k1 = min(n, k0 + len);
   iir_segment(tile + j, n, L, k0, k1, j < ncol && k0 < k1);
   __syncthreads();
-  for (int k = seg; k < n; k += kSegs)
-    if (j < ncol) out[base + (int64_t)k * line_stride + j] = tile[k * L + j];
+  if (j < ncol) {
+    TOut* q = out + base_out + j;
+#pragma unroll 8
+    for (int k = seg; k < n; k += kSegs) q[(int64_t)k * S.line_out] = (TOut)tile[k * L + j];
+  }
 }
 
 // lines along the contiguous axis.  grid = ceil(n_rows / L), block = 256, tile [L][n | 1]
@@ -285,6 +296,7 @@ prefilter_rows_seg(double* __restrict__ data, int n, int64_t n_rows) {
 }
 
 // fallback for lines too long for shared memory: sweep in global memory
+// (double output only: the sweep runs in place in global memory)
 template <typename TIn>
 __global__ void prefilter_cols_global(const TIn* __restrict__ in, double* __restrict__ out, int n,
                                       int64_t line_stride, int n_cols, int64_t outer_stride) {
@@ -658,6 +670,162 @@ march3_tma_kernel(const __grid_constant__ CUtensorMap tmap, int xb, const ZWin* 
   }
 }
 
+// ------------------------------------------------- x axis: prefilter + interpolation in one pass
+// The rows of the (z,y)-filtered float32 volume are prefiltered along x in a shared-memory tile
+// (segment-parallel, float64) and interpolated to the nx output columns at once: what leaves the SM
+// is the x-RESAMPLED volume [rows][nx] in float64, so the march that follows only interpolates along
+// y and z and reads its planes as ready-made TMA boxes.  grid = ceil(n_rows / L), block = 256.
+template <int L>
+__global__ void __launch_bounds__(256)
+rows_prefilter_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* __restrict__ out,
+                             int64_t out_pitch, int n, int nx, int64_t n_rows, const Tap* __restrict__ tx) {
+  extern __shared__ double tile[];
+  constexpr int kSegs = 256 / L;
+  const int pitch = n | 1;
+  const int64_t row0 = (int64_t)blockIdx.x * L;
+  const int nrow = (int)min((int64_t)L, n_rows - row0);
+  const float* g = in + row0 * in_pitch;
+  for (int r = threadIdx.x >> 5; r < nrow; r += 8) {
+    const float* gr = g + (int64_t)r * in_pitch;
+#pragma unroll 4
+    for (int k = threadIdx.x & 31; k < n; k += 32) tile[r * pitch + k] = (double)gr[k] * kGain;
+  }
+  __syncthreads();
+  {
+    const int r = threadIdx.x & (L - 1), seg = threadIdx.x / L;
+    const int len = (n + kSegs - 1) / kSegs;
+    const int k0 = seg * len, k1 = min(n, k0 + len);
+    iir_segment(tile + r * pitch, n, 1, k0, k1, r < nrow && k0 < k1);
+  }
+  __syncthreads();
+  // a thread owns output columns x, x + 256, ...: its taps stay in registers while it walks the rows
+  for (int x = threadIdx.x; x < nx; x += 256) {
+    const Tap T = tx[x];
+    double* o = out + row0 * out_pitch + x;
+#pragma unroll 4
+    for (int r = 0; r < nrow; ++r) {
+      const double* row = tile + r * pitch;
+      o[(int64_t)r * out_pitch] = T.w[0] * row[T.idx[0]] + T.w[1] * row[T.idx[1]] + T.w[2] * row[T.idx[2]] +
+                                  T.w[3] * row[T.idx[3]];
+    }
+  }
+}
+
+// ------------------------------------------------- marching y/z interpolation, TMA-fed
+// Input: the x-resampled float64 volume [sz_l][sy][nxp] (rows_prefilter_interp_kernel).  A CTA owns an
+// [8 y x 64 x] output column and marches along z: each source plane's rows arrive as ONE
+// cp.async.bulk.tensor box ([ROWS y] x [64 x]) in a kYzStages-deep mbarrier ring issued by one elected
+// thread; y-interpolation reads the box in place into a 4-plane register window and every output plane
+// is 4 FMAs from that window.  ~4 shared loads and ~10 FMAs per output voxel.
+constexpr int kYzStages = 8;
+
+template <int NI>
+__global__ void __launch_bounds__(256, 4)
+march_yz_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ZWin* __restrict__ zw,
+                    const Tap* __restrict__ ty, float* __restrict__ dst, int ny, int nx, int nz_local, int zchunk) {
+  constexpr int TX = 64, TY = 8, ROWS = NI * 4;
+  constexpr uint32_t kStageBytes = ROWS * TX * 8;
+  extern __shared__ uint8_t march_smem[];
+  __shared__ __align__(8) uint64_t full[kYzStages];
+  __shared__ int s_lo;
+  const uint32_t ring_base = (smem_addr(march_smem) + 127u) & ~127u;
+  const int t = threadIdx.x;
+  const int lx = t & (TX - 1), lr = t >> 6;
+  const int x0 = blockIdx.x * TX, x = x0 + lx;
+  const int y0 = blockIdx.y * TY;
+  const int z_begin = blockIdx.z * zchunk, z_end = min(nz_local, z_begin + zchunk);
+  if (z_begin >= z_end) return;
+  if (t == 0) {
+    s_lo = 0x7fffffff;
+    for (int i = 0; i < kYzStages; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&full[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t < TY * 4) {   // lowest source row any output row of this tile taps (zero-weight taps, D11, excluded)
+    const int r = min(y0 + (t >> 2), ny - 1);
+    if (ty[r].w[t & 3] != 0.0) atomicMin(&s_lo, ty[r].idx[t & 3]);
+  }
+  __syncthreads();
+  const int lo_y = (s_lo == 0x7fffffff) ? 0 : s_lo;
+  double wy[2][4];
+  uint32_t a_rd[2][4];     // byte offset of y tap m of output o inside a ring stage
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const Tap T = ty[min(y0 + lr + 4 * o, ny - 1)];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      wy[o][m] = T.w[m];
+      const int iym = (T.w[m] != 0.0) ? min(ROWS - 1, T.idx[m] - lo_y) : 0;
+      a_rd[o][m] = (uint32_t)((iym * TX + lx) * 8);
+    }
+  }
+  double v[2][4];
+#pragma unroll
+  for (int o = 0; o < 2; ++o)
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[o][m] = 0.0;
+  const int p_start = zw[z_begin].base, p_last = zw[z_end - 1].base + 3;
+  auto issue = [&](int p, int sidx) {
+    const uint32_t bar = smem_addr(&full[sidx]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kStageBytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(ring_base + (uint32_t)sidx * kStageBytes), "l"(&tmap), "r"(x0), "r"(lo_y), "r"(p), "r"(bar)
+        : "memory");
+  };
+  if (t == 0)
+    for (int i = 0; i < kYzStages && p_start + i <= p_last; ++i) issue(p_start + i, i);
+  auto lds = [](uint32_t addr) {
+    double d;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(d) : "r"(addr));
+    return d;
+  };
+  const int64_t out_plane = (int64_t)ny * nx;
+  float* outp[2];
+  bool outok[2];
+#pragma unroll
+  for (int o = 0; o < 2; ++o) {
+    const int y = y0 + lr + 4 * o;
+    outok[o] = x < nx && y < ny;
+    outp[o] = dst + ((int64_t)z_begin * ny + min(y, ny - 1)) * nx + min(x, nx - 1);
+  }
+  int zc = z_begin;
+  int next_emit = zw[zc].base + 3;
+  int sidx = 0;
+  uint32_t phase = 0;
+  for (int p = p_start; p <= p_last; ++p) {
+    mbar_wait(smem_addr(&full[sidx]), phase);
+    const uint32_t raw = ring_base + (uint32_t)sidx * kStageBytes;
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const double vn = wy[o][0] * lds(raw + a_rd[o][0]) + wy[o][1] * lds(raw + a_rd[o][1]) +
+                        wy[o][2] * lds(raw + a_rd[o][2]) + wy[o][3] * lds(raw + a_rd[o][3]);
+      v[o][0] = v[o][1];
+      v[o][1] = v[o][2];
+      v[o][2] = v[o][3];
+      v[o][3] = vn;
+    }
+    __syncthreads();   // every thread has read ring stage sidx: it may be refilled
+    if (t == 0 && p + kYzStages <= p_last) issue(p + kYzStages, sidx);
+    while (zc < z_end && next_emit <= p) {
+      const ZWin Wz = zw[zc];
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {
+        const double acc = Wz.w[0] * v[o][0] + Wz.w[1] * v[o][1] + Wz.w[2] * v[o][2] + Wz.w[3] * v[o][3];
+        if (outok[o]) st_stream(outp[o], (float)acc);
+        outp[o] += out_plane;
+      }
+      ++zc;
+      if (zc < z_end) next_emit = zw[zc].base + 3;
+    }
+    if (++sidx == kYzStages) {
+      sidx = 0;
+      phase ^= 1u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128)
 gather1_kernel(const float* __restrict__ src, int sy, int sx, const Tap* __restrict__ tz,
                const Tap* __restrict__ ty, const Tap* __restrict__ tx, float* __restrict__ dst, int ny,
@@ -700,33 +868,46 @@ static int g_force_generic = 0;   // tests: run the general kernels on shapes th
 
 constexpr size_t kMaxTileBytes = 200 * 1024;
 
-template <typename TIn>
-static int launch_cols(const TIn* in, double* out, int n, int64_t line_stride, int n_cols,
-                       int64_t outer_stride, int n_outer, cudaStream_t st) {
+template <typename TIn, typename TOut>
+static int launch_cols(const TIn* in, TOut* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
   if (n_cols <= 0 || n_outer <= 0 || n <= 0) return MICA_OK;
   size_t per_col = (size_t)n * sizeof(double);
   if (!g_force_generic && n >= kMinSegLine && per_col * 32 <= kMaxTileBytes) {
     if (prefilter_lines() == 16) {
       size_t smem = per_col * 16;
-      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prefilter_cols_seg<TIn, 16><<<dim3((n_cols + 15) / 16, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, TOut, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_cols_seg<TIn, TOut, 16><<<dim3((n_cols + 15) / 16, n_outer), 256, smem, st>>>(in, out, n, n_cols, S);
     } else {
       size_t smem = per_col * 32;
-      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      prefilter_cols_seg<TIn, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+      MICA_CUDA(cudaFuncSetAttribute(prefilter_cols_seg<TIn, TOut, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      prefilter_cols_seg<TIn, TOut, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, n_cols, S);
     }
   } else if (per_col * 32 <= kMaxTileBytes) {
     size_t smem = per_col * 32;
-    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prefilter_cols<TIn, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, TOut, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefilter_cols<TIn, TOut, 32><<<dim3((n_cols + 31) / 32, n_outer), 256, smem, st>>>(in, out, n, n_cols, S);
   } else if (per_col * 8 <= kMaxTileBytes) {
     size_t smem = per_col * 8;
-    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    prefilter_cols<TIn, 8><<<dim3((n_cols + 7) / 8, n_outer), 256, smem, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    MICA_CUDA(cudaFuncSetAttribute(prefilter_cols<TIn, TOut, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    prefilter_cols<TIn, TOut, 8><<<dim3((n_cols + 7) / 8, n_outer), 256, smem, st>>>(in, out, n, n_cols, S);
   } else {
-    prefilter_cols_global<TIn><<<dim3((n_cols + 127) / 128, n_outer), 128, 0, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+    return set_error(MICA_ERR_INVALID, "line of %d samples too long for the shared-memory prefilter", n);
   }
   MICA_LAUNCH_CHECK("prefilter_cols");
+  return MICA_OK;
+}
+
+// the old all-float64 path keeps its global-memory sweep for lines that fit no tile
+template <typename TIn>
+static int launch_cols_f64(const TIn* in, double* out, int n, int64_t line_stride, int n_cols,
+                           int64_t outer_stride, int n_outer, cudaStream_t st) {
+  if (n_cols <= 0 || n_outer <= 0 || n <= 0) return MICA_OK;
+  if ((size_t)n * sizeof(double) * 8 <= kMaxTileBytes) {
+    ColStrides S{line_stride, line_stride, outer_stride, outer_stride};
+    return launch_cols<TIn, double>(in, out, n, n_cols, n_outer, S, st);
+  }
+  prefilter_cols_global<TIn><<<dim3((n_cols + 127) / 128, n_outer), 128, 0, st>>>(in, out, n, line_stride, n_cols, outer_stride);
+  MICA_LAUNCH_CHECK("prefilter_cols_global");
   return MICA_OK;
 }
 
@@ -778,10 +959,31 @@ extern "C" int mica_resample_force_generic(int on) {
   return was;
 }
 
+// The fast order-3 path: z and y prefilters write float32 coefficients (padded row pitch), the x pass
+// prefilters and interpolates rows into a float64 volume [sz_l][sy][nxp], the march interpolates y and z.
+static bool fast_path_ok(int src_nz_local, int sy, int sx, int ny, int nx) {
+  if (g_force_generic || getenv("MICA_NO_TMA") || getenv("MICA_RESAMPLE_OLD")) return false;
+  if (src_nz_local < 4 || sy < 4 || sx < kMinSegLine) return false;
+  if ((size_t)(sx | 1) * sizeof(double) * 16 > kMaxTileBytes) return false;            // x tile of 16 rows
+  if ((size_t)src_nz_local * sizeof(double) * 8 > kMaxTileBytes) return false;          // z lines fit a tile
+  if ((size_t)sy * sizeof(double) * 8 > kMaxTileBytes) return false;
+  const double zoom_y = ny > 1 ? (double)(sy - 1) / (double)(ny - 1) : 1.0;
+  if ((int)floor(7.0 * zoom_y) + 5 > 16) return false;                                    // y span of an 8-row tile
+  return tensor_map_encode_fn() != nullptr;
+}
+static int64_t pitch_f32(int sx) { return ((int64_t)sx + 3) / 4 * 4; }
+static int64_t pitch_f64(int nx) { return ((int64_t)nx + 1) / 2 * 2; }
+
 extern "C" size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, int ny, int nx, int order) {
   size_t taps = align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256) + align_up((size_t)nz * sizeof(ZWin), 256);
-  size_t coeff = (order == 3) ? align_up((size_t)src_nz_local * sy * sx * sizeof(double), 256) : 0;
-  return taps + coeff + 256;
+  size_t coeff = 0;
+  if (order == 3) {
+    coeff = align_up((size_t)src_nz_local * sy * sx * sizeof(double), 256);                 // general path
+    const size_t fast = align_up((size_t)src_nz_local * sy * pitch_f32(sx) * sizeof(float), 256) +
+                        align_up((size_t)src_nz_local * sy * pitch_f64(nx) * sizeof(double), 256);
+    if (fast > coeff) coeff = fast;
+  }
+  return taps + coeff + 512;
 }
 
 extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int sx, int src_z0, int src_nz_local,
@@ -813,14 +1015,63 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
   MICA_LAUNCH_CHECK("taps_kernel(x)");
 
   dim3 grid((nx + 127) / 128, ny, dst_nz_local);
-  if (order == 3) {
+  if (order == 3 && fast_path_ok(src_nz_local, sy, sx, ny, nx)) {
+    const int64_t plane = (int64_t)sy * sx;
+    MICA_REQUIRE(plane <= 0x7fffffffLL && src_nz_local <= 65535 && sy <= 65535, "source plane too large");
+    const int64_t p32 = pitch_f32(sx), p64 = pitch_f64(nx);
+    float* c32 = (float*)coeff;
+    double* xr = (double*)((char*)coeff + align_up((size_t)src_nz_local * sy * p32 * sizeof(float), 256));
+    // axis 0 (z): columns (y, x0..x0+15) of length src_nz_local; float32 in (row pitch sx), float32 out (pitch p32)
+    int rc = launch_cols<float, float>(src, c32, src_nz_local, sx, sy, ColStrides{plane, sy * p32, sx, p32}, st);
+    if (rc) return rc;
+    // axis 1 (y): in place, per z plane, lines of length sy with stride p32
+    rc = launch_cols<float, float>(c32, c32, sy, sx, src_nz_local, ColStrides{p32, p32, sy * p32, sy * p32}, st);
+    if (rc) return rc;
+    // axis 2 (x): prefilter + interpolate the rows -> x-resampled float64 volume
+    {
+      const int64_t n_rows = (int64_t)src_nz_local * sy;
+      const size_t smem = (size_t)(sx | 1) * sizeof(double) * 16;
+      MICA_CUDA(cudaFuncSetAttribute(rows_prefilter_interp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      rows_prefilter_interp_kernel<16><<<(unsigned)ceil_div64(n_rows, 16), 256, smem, st>>>(c32, p32, xr, p64, sx, nx, n_rows, tx);
+      MICA_LAUNCH_CHECK("rows_prefilter_interp_kernel");
+    }
+    zwin_kernel<<<(dst_nz_local + 127) / 128, 128, 0, st>>>(tz, zw, dst_nz_local, src_nz_local);
+    MICA_LAUNCH_CHECK("zwin_kernel");
+    const int xt = (nx + 63) / 64, yt = (ny + 7) / 8;
+    int nzc = (8 * kNumSMs + xt * yt - 1) / (xt * yt);
+    nzc = nzc < 1 ? 1 : nzc;
+    if (nzc > (dst_nz_local + 15) / 16) nzc = (dst_nz_local + 15) / 16;
+    const int zchunk = (dst_nz_local + nzc - 1) / nzc;
+    dim3 mgrid(xt, yt, (dst_nz_local + zchunk - 1) / zchunk);
+    MICA_REQUIRE(yt <= 65535 && mgrid.z <= 65535, "output too large for the launch grid");
+    const double zoom_y = ny > 1 ? (double)(sy - 1) / (double)(ny - 1) : 1.0;
+    const int rows = ((int)floor(7.0 * zoom_y) + 5) <= 12 ? 12 : 16;
+    CUtensorMap tmap;
+    cuuint64_t gdim[3] = {(cuuint64_t)p64, (cuuint64_t)sy, (cuuint64_t)src_nz_local};
+    cuuint64_t gstr[2] = {(cuuint64_t)p64 * 8, (cuuint64_t)sy * p64 * 8};
+    cuuint32_t box[3] = {64, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = tensor_map_encode_fn()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)xr, gdim, gstr, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return set_error(MICA_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    const size_t smem = (size_t)kYzStages * rows * 64 * 8 + 128;
+    if (rows == 12) {
+      MICA_CUDA(cudaFuncSetAttribute(march_yz_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      march_yz_tma_kernel<3><<<mgrid, 256, smem, st>>>(tmap, zw, ty, dst, ny, nx, dst_nz_local, zchunk);
+    } else {
+      MICA_CUDA(cudaFuncSetAttribute(march_yz_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      march_yz_tma_kernel<4><<<mgrid, 256, smem, st>>>(tmap, zw, ty, dst, ny, nx, dst_nz_local, zchunk);
+    }
+    MICA_LAUNCH_CHECK("march_yz_tma_kernel");
+  } else if (order == 3) {
     const int64_t plane = (int64_t)sy * sx;
     MICA_REQUIRE(plane <= 0x7fffffffLL && src_nz_local <= 65535, "source plane too large");
     // axis 0 (z): lines of length src_nz_local, stride plane; reads float32, writes float64
-    int rc = launch_cols<float>(src, coeff, src_nz_local, plane, (int)plane, 0, 1, st);
+    int rc = launch_cols_f64<float>(src, coeff, src_nz_local, plane, (int)plane, 0, 1, st);
     if (rc) return rc;
     // axis 1 (y): per z plane, lines of length sy, stride sx
-    rc = launch_cols<double>(coeff, coeff, sy, sx, sx, plane, src_nz_local, st);
+    rc = launch_cols_f64<double>(coeff, coeff, sy, sx, sx, plane, src_nz_local, st);
     if (rc) return rc;
     // axis 2 (x): contiguous rows
     rc = launch_rows(coeff, sx, (int64_t)src_nz_local * sy, st);
