@@ -226,7 +226,7 @@ __device__ __forceinline__ void iir_segment(double* line, int n, int stride, int
         st = (z / (z * z - 1.0)) * (line[(n - 1) * stride] + z * line[(n - 2) * stride]);
         k = n - 2;
       }
-      for (; k >= k1; --k) st = z * (st - line[k * stride]);
+      for (; k >= k1; --k) st = fma(z, st, -z * line[k * stride]);   // z (st - c): one FMA on the chain
     }
   }
   __syncthreads();
@@ -239,7 +239,7 @@ __device__ __forceinline__ void iir_segment(double* line, int n, int stride, int
     }
 #pragma unroll 4
     for (; k >= k0; --k) {
-      st = z * (st - line[k * stride]);
+      st = fma(z, st, -z * line[k * stride]);
       line[k * stride] = st;
     }
   }
@@ -516,6 +516,166 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   }
+}
+
+// ------------------------------------------------- cp.async-pipelined prefilter passes (fast path)
+// The passes above load a tile, sweep it, store it -- and reach ~30 % of the HBM bandwidth because the three
+// phases of a CTA do not overlap.  Here a persistent CTA walks over its tiles with the float32 input of the
+// NEXT tile(s) already in flight (cp.async into a small staging ring: no registers, any alignment), converts
+// the staged tile into one float64 work tile, sweeps it (iir_segment, exact float64 as before) and writes
+// the result straight from the work tile.
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kPipeStages = 2;
+
+// lines along a strided axis (z or y): tile = [n samples] x [L columns]; tiles are numbered
+// outer * x_tiles + x_tile.  float32 in, float32 out.  block = THREADS, dynamic smem =
+// n * L * (4 * kPipeStages + 8) bytes.
+template <int L, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+cols_pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, int n_outer, ColStrides S) {
+  extern __shared__ __align__(16) uint8_t pipe_smem[];
+  constexpr int kSegs = THREADS / L;
+  double* work = reinterpret_cast<double*>(pipe_smem);                       // [n][L]
+  float* stage0 = reinterpret_cast<float*>(pipe_smem + (size_t)n * L * 8);   // kPipeStages x [n][L]
+  const uint32_t stage_a = smem_addr(stage0);
+  const int x_tiles = (n_cols + L - 1) / L;
+  const long long n_tiles = (long long)x_tiles * n_outer;
+  const bool in16 = ((((uintptr_t)in) | ((uintptr_t)(S.line_in * 4)) | ((uintptr_t)(S.outer_in * 4))) & 15) == 0;
+  const bool out16 = ((((uintptr_t)out) | ((uintptr_t)(S.line_out * 4)) | ((uintptr_t)(S.outer_out * 4))) & 15) == 0;
+
+  auto prefetch = [&](long long tile, int sidx) {
+    if (tile < n_tiles) {
+      const int xt = (int)(tile % x_tiles);
+      const long long o = tile / x_tiles;
+      const int col0 = xt * L, ncol = min(L, n_cols - col0);
+      const float* g = in + o * S.outer_in + col0;
+      const uint32_t dst = stage_a + (uint32_t)sidx * (uint32_t)(n * L * 4);
+      if (in16 && ncol == L) {
+        for (int e = threadIdx.x; e < n * (L / 4); e += THREADS) {
+          const int k = e / (L / 4), c = e - k * (L / 4);
+          cp_async16(dst + (uint32_t)((k * L + 4 * c) * 4), g + (int64_t)k * S.line_in + 4 * c);
+        }
+      } else {
+        for (int e = threadIdx.x; e < n * L; e += THREADS) {
+          const int k = e / L, j = e - k * L;
+          if (j < ncol) cp_async4(dst + (uint32_t)(e * 4), g + (int64_t)k * S.line_in + j);
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
+  long long tile = blockIdx.x;
+  for (int i = 0; i < kPipeStages - 1; ++i) prefetch(tile + (long long)i * gridDim.x, i);
+  int sidx = 0;
+  const int j = threadIdx.x & (L - 1), seg = threadIdx.x / L;
+  const int len = (n + kSegs - 1) / kSegs;
+  const int k0 = seg * len, k1 = min(n, k0 + len);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    // keep the ring full: the load of tile + (stages-1) strides goes into the stage freed last iteration
+    prefetch(tile + (long long)(kPipeStages - 1) * gridDim.x, (sidx + kPipeStages - 1) % kPipeStages);
+    cp_async_wait<kPipeStages - 1>();
+    __syncthreads();                                   // this tile's staged samples are visible to everybody
+    const float* st = stage0 + (size_t)sidx * n * L;
+    for (int e = threadIdx.x; e < n * L; e += THREADS) work[e] = (double)st[e] * kGain;
+    __syncthreads();
+    const int xt = (int)(tile % x_tiles);
+    const long long o = tile / x_tiles;
+    const int col0 = xt * L, ncol = min(L, n_cols - col0);
+    iir_segment(work + j, n, L, k0, k1, j < ncol && k0 < k1);
+    __syncthreads();
+    float* q = out + o * S.outer_out + col0;
+    if (out16 && ncol == L) {
+      for (int e = threadIdx.x; e < n * (L / 4); e += THREADS) {
+        const int k = e / (L / 4), c = e - k * (L / 4);
+        const double* w = work + k * L + 4 * c;
+        const float4 v = make_float4((float)w[0], (float)w[1], (float)w[2], (float)w[3]);
+        *reinterpret_cast<float4*>(q + (int64_t)k * S.line_out + 4 * c) = v;
+      }
+    } else {
+      for (int e = threadIdx.x; e < n * L; e += THREADS) {
+        const int k = e / L, jj = e - k * L;
+        if (jj < ncol) q[(int64_t)k * S.line_out + jj] = (float)work[e];
+      }
+    }
+    __syncthreads();                                   // work tile and stage sidx are free again
+    sidx = (sidx + 1) % kPipeStages;
+  }
+  cp_async_wait<0>();
+}
+
+// x axis: rows of the (z,y)-filtered float32 volume (row pitch in_pitch, a multiple of 4) are staged by
+// cp.async, prefiltered in a float64 work tile and interpolated to the nx output columns at once: what leaves
+// the SM is the x-RESAMPLED float64 volume [rows][out_pitch], so the march that follows only interpolates
+// along y and z.  dynamic smem = L * (n | 1) * 8 + kPipeStages * L * in_pitch * 4 bytes.
+template <int L, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+rows_pipe_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* __restrict__ out, int64_t out_pitch,
+                        int n, int nx, int64_t n_rows, const Tap* __restrict__ tx) {
+  extern __shared__ __align__(16) uint8_t pipe_smem[];
+  constexpr int kSegs = THREADS / L;
+  const int pitch = n | 1;
+  const int sp = (int)in_pitch;                                             // staging row pitch (floats)
+  double* work = reinterpret_cast<double*>(pipe_smem);                      // [L][pitch]
+  float* stage0 = reinterpret_cast<float*>(pipe_smem + (((size_t)L * pitch * 8 + 15) & ~(size_t)15));
+  const uint32_t stage_a = smem_addr(stage0);
+  const long long n_tiles = (n_rows + L - 1) / L;
+  const int chunks = sp / 4;                                                // 16-byte chunks per row
+
+  auto prefetch = [&](long long tile, int sidx) {
+    if (tile < n_tiles) {
+      const int64_t row0 = tile * L;
+      const int nrow = (int)min((int64_t)L, n_rows - row0);
+      const float* g = in + row0 * in_pitch;
+      const uint32_t dst = stage_a + (uint32_t)sidx * (uint32_t)(L * sp * 4);
+      for (int e = threadIdx.x; e < nrow * chunks; e += THREADS)             // rows are contiguous: one flat copy
+        cp_async16(dst + (uint32_t)(e * 16), g + (int64_t)e * 4);
+    }
+    cp_async_commit();
+  };
+
+  long long tile = blockIdx.x;
+  for (int i = 0; i < kPipeStages - 1; ++i) prefetch(tile + (long long)i * gridDim.x, i);
+  int sidx = 0;
+  const int r_seg = threadIdx.x & (L - 1), seg = threadIdx.x / L;
+  const int len = (n + kSegs - 1) / kSegs;
+  const int k0 = seg * len, k1 = min(n, k0 + len);
+  for (; tile < n_tiles; tile += gridDim.x) {
+    prefetch(tile + (long long)(kPipeStages - 1) * gridDim.x, (sidx + kPipeStages - 1) % kPipeStages);
+    cp_async_wait<kPipeStages - 1>();
+    __syncthreads();
+    const int64_t row0 = tile * L;
+    const int nrow = (int)min((int64_t)L, n_rows - row0);
+    const float* st = stage0 + (size_t)sidx * L * sp;
+    for (int r = threadIdx.x >> 5; r < nrow; r += THREADS / 32)
+      for (int k = threadIdx.x & 31; k < n; k += 32) work[r * pitch + k] = (double)st[r * sp + k] * kGain;
+    __syncthreads();
+    iir_segment(work + r_seg * pitch, n, 1, k0, k1, r_seg < nrow && k0 < k1);
+    __syncthreads();
+    // a thread owns output columns x, x + THREADS, ...: its taps stay in registers while it walks the rows
+    for (int x = threadIdx.x; x < nx; x += THREADS) {
+      const Tap T = tx[x];
+      double* o = out + row0 * out_pitch + x;
+#pragma unroll 4
+      for (int r = 0; r < nrow; ++r) {
+        const double* row = work + r * pitch;
+        o[(int64_t)r * out_pitch] = T.w[0] * row[T.idx[0]] + T.w[1] * row[T.idx[1]] + T.w[2] * row[T.idx[2]] +
+                                    T.w[3] * row[T.idx[3]];
+      }
+    }
+    __syncthreads();
+    sidx = (sidx + 1) % kPipeStages;
+  }
+  cp_async_wait<0>();
 }
 
 // grid = (ceil(nx / 64), ceil(ny / 8), z chunks), block = 256; dynamic smem = ring + 1 KB alignment slack
@@ -961,18 +1121,66 @@ extern "C" int mica_resample_force_generic(int on) {
 
 // The fast order-3 path: z and y prefilters write float32 coefficients (padded row pitch), the x pass
 // prefilters and interpolates rows into a float64 volume [sz_l][sy][nxp], the march interpolates y and z.
+constexpr size_t kPipeSmemMax = 220 * 1024;
+static int64_t pitch_f32(int sx) { return ((int64_t)sx + 3) / 4 * 4; }
+static int64_t pitch_f64(int nx) { return ((int64_t)nx + 1) / 2 * 2; }
+static size_t cols_pipe_smem(int n, int L) { return (size_t)n * L * (4 * kPipeStages + 8); }
+static size_t rows_pipe_smem(int n, int L) {
+  return (((size_t)L * (n | 1) * 8 + 15) & ~(size_t)15) + (size_t)kPipeStages * L * pitch_f32(n) * 4;
+}
+
 static bool fast_path_ok(int src_nz_local, int sy, int sx, int ny, int nx) {
   if (g_force_generic || getenv("MICA_NO_TMA") || getenv("MICA_RESAMPLE_OLD")) return false;
-  if (src_nz_local < 4 || sy < 4 || sx < kMinSegLine) return false;
-  if ((size_t)(sx | 1) * sizeof(double) * 16 > kMaxTileBytes) return false;            // x tile of 16 rows
-  if ((size_t)src_nz_local * sizeof(double) * 8 > kMaxTileBytes) return false;          // z lines fit a tile
-  if ((size_t)sy * sizeof(double) * 8 > kMaxTileBytes) return false;
+  if (src_nz_local < kMinSegLine || sy < kMinSegLine || sx < kMinSegLine) return false;   // segment-parallel sweeps
+  if (cols_pipe_smem(src_nz_local, 8) > kPipeSmemMax || cols_pipe_smem(sy, 8) > kPipeSmemMax ||
+      rows_pipe_smem(sx, 8) > kPipeSmemMax)
+    return false;
   const double zoom_y = ny > 1 ? (double)(sy - 1) / (double)(ny - 1) : 1.0;
   if ((int)floor(7.0 * zoom_y) + 5 > 16) return false;                                    // y span of an 8-row tile
   return tensor_map_encode_fn() != nullptr;
 }
-static int64_t pitch_f32(int sx) { return ((int64_t)sx + 3) / 4 * 4; }
-static int64_t pitch_f64(int nx) { return ((int64_t)nx + 1) / 2 * 2; }
+
+// persistent grid: as many CTAs as fit (shared memory bound), tiles dealt round-robin
+template <int L, int THREADS>
+static int launch_cols_pipe_t(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
+  const size_t smem = cols_pipe_smem(n, L);
+  MICA_CUDA(cudaFuncSetAttribute(cols_pipe_kernel<L, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / THREADS ? 2048 / THREADS : per_sm);
+  const long long tiles = (long long)((n_cols + L - 1) / L) * n_outer;
+  long long grid = (long long)kNumSMs * per_sm;
+  if (grid > tiles) grid = tiles;
+  cols_pipe_kernel<L, THREADS><<<(unsigned)grid, THREADS, smem, st>>>(in, out, n, n_cols, n_outer, S);
+  MICA_LAUNCH_CHECK("cols_pipe_kernel");
+  return MICA_OK;
+}
+static int launch_cols_pipe(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
+  if (n_cols <= 0 || n_outer <= 0) return MICA_OK;
+  if (cols_pipe_smem(n, 16) <= 110 * 1024) return launch_cols_pipe_t<16, 256>(in, out, n, n_cols, n_outer, S, st);
+  if (cols_pipe_smem(n, 16) <= kPipeSmemMax) return launch_cols_pipe_t<16, 512>(in, out, n, n_cols, n_outer, S, st);
+  return launch_cols_pipe_t<8, 512>(in, out, n, n_cols, n_outer, S, st);
+}
+template <int L, int THREADS>
+static int launch_rows_pipe_t(const float* in, int64_t in_pitch, double* out, int64_t out_pitch, int n, int nx,
+                              int64_t n_rows, const Tap* tx, cudaStream_t st) {
+  const size_t smem = rows_pipe_smem(n, L);
+  MICA_CUDA(cudaFuncSetAttribute(rows_pipe_interp_kernel<L, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 2048 / THREADS ? 2048 / THREADS : per_sm);
+  const long long tiles = (n_rows + L - 1) / L;
+  long long grid = (long long)kNumSMs * per_sm;
+  if (grid > tiles) grid = tiles;
+  rows_pipe_interp_kernel<L, THREADS><<<(unsigned)grid, THREADS, smem, st>>>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx);
+  MICA_LAUNCH_CHECK("rows_pipe_interp_kernel");
+  return MICA_OK;
+}
+static int launch_rows_pipe(const float* in, int64_t in_pitch, double* out, int64_t out_pitch, int n, int nx,
+                            int64_t n_rows, const Tap* tx, cudaStream_t st) {
+  if (n_rows <= 0) return MICA_OK;
+  if (rows_pipe_smem(n, 16) <= 110 * 1024) return launch_rows_pipe_t<16, 256>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
+  if (rows_pipe_smem(n, 16) <= kPipeSmemMax) return launch_rows_pipe_t<16, 512>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
+  return launch_rows_pipe_t<8, 512>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
+}
 
 extern "C" size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, int ny, int nx, int order) {
   size_t taps = align_up((size_t)(nz + ny + nx) * sizeof(Tap), 256) + align_up((size_t)nz * sizeof(ZWin), 256);
@@ -1022,13 +1230,19 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
     float* c32 = (float*)coeff;
     double* xr = (double*)((char*)coeff + align_up((size_t)src_nz_local * sy * p32 * sizeof(float), 256));
     // axis 0 (z): columns (y, x0..x0+15) of length src_nz_local; float32 in (row pitch sx), float32 out (pitch p32)
-    int rc = launch_cols<float, float>(src, c32, src_nz_local, sx, sy, ColStrides{plane, sy * p32, sx, p32}, st);
+    const bool pipe = !getenv("MICA_RESAMPLE_NOPIPE");
+    int rc = pipe ? launch_cols_pipe(src, c32, src_nz_local, sx, sy, ColStrides{plane, sy * p32, sx, p32}, st)
+                  : launch_cols<float, float>(src, c32, src_nz_local, sx, sy, ColStrides{plane, sy * p32, sx, p32}, st);
     if (rc) return rc;
     // axis 1 (y): in place, per z plane, lines of length sy with stride p32
-    rc = launch_cols<float, float>(c32, c32, sy, sx, src_nz_local, ColStrides{p32, p32, sy * p32, sy * p32}, st);
+    rc = pipe ? launch_cols_pipe(c32, c32, sy, sx, src_nz_local, ColStrides{p32, p32, sy * p32, sy * p32}, st)
+              : launch_cols<float, float>(c32, c32, sy, sx, src_nz_local, ColStrides{p32, p32, sy * p32, sy * p32}, st);
     if (rc) return rc;
     // axis 2 (x): prefilter + interpolate the rows -> x-resampled float64 volume
-    {
+    if (pipe) {
+      rc = launch_rows_pipe(c32, p32, xr, p64, sx, nx, (int64_t)src_nz_local * sy, tx, st);
+      if (rc) return rc;
+    } else {
       const int64_t n_rows = (int64_t)src_nz_local * sy;
       const size_t smem = (size_t)(sx | 1) * sizeof(double) * 16;
       MICA_CUDA(cudaFuncSetAttribute(rows_prefilter_interp_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
