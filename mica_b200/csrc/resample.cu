@@ -245,6 +245,74 @@ __device__ __forceinline__ void iir_segment(double* line, int n, int stride, int
   }
 }
 
+// Register-blocked variant for the pipelined passes.  iir_segment walks shared memory inside the
+// dependent chain (load -> FMA -> store per sample: ncu shows the warps waiting on the shared-memory
+// scoreboard 5 cycles per issued instruction).  Here a thread first pulls its segment (<= LMAX samples) and
+// its warm-up samples into registers with independent loads, runs both recursions register to register and
+// writes the segment back once per sweep.  H = warm-up horizon: |pole|^20 = 4e-12, four orders below the
+// float32 rounding of what these passes produce.  STRIDE is the (compile-time) distance between samples.
+template <int LMAX, int H, int STRIDE>
+__device__ __forceinline__ void iir_segment_reg(double* line, int n, int k0, int k1, bool active) {
+  const double z = kPole;
+  double s[LMAX];
+  double st = 0.0;
+  if (active) {
+    double w[H];
+#pragma unroll
+    for (int m = 0; m < H; ++m) {      // samples k0-1-m, mirrored below 0
+      int idx = k0 - 1 - m;
+      idx = idx < 0 ? -idx : idx;
+      w[m] = line[idx * STRIDE];
+    }
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i) s[i] = (k0 + i < k1) ? line[(k0 + i) * STRIDE] : 0.0;
+#pragma unroll
+    for (int m = H - 1; m >= 0; --m) st = fma(z, st, w[m]);
+  }
+  __syncthreads();   // every read of raw samples is done before anyone overwrites them
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < LMAX; ++i)
+      if (k0 + i < k1) {
+        st = fma(z, st, s[i]);
+        s[i] = st;
+        line[(k0 + i) * STRIDE] = st;   // the causal result: neighbours warm up on it
+      }
+  }
+  __syncthreads();
+  bool at_end = false;
+  if (active) {      // anticausal state just above the segment
+    if (k1 >= n) {
+      at_end = true;
+    } else if (k1 + H >= n) {   // the exact end initialisation is within reach: start from it
+      st = (z / (z * z - 1.0)) * (line[(n - 1) * STRIDE] + z * line[(n - 2) * STRIDE]);
+      for (int k = n - 2; k >= k1; --k) st = fma(z, st, -z * line[k * STRIDE]);
+    } else {
+      double w[H];
+#pragma unroll
+      for (int m = 0; m < H; ++m) w[m] = line[(k1 + m) * STRIDE];
+      st = 0.0;
+#pragma unroll
+      for (int m = H - 1; m >= 0; --m) st = fma(z, st, -z * w[m]);
+    }
+  }
+  __syncthreads();   // every warm-up read of causal results is done
+  if (active) {
+    const int last = k1 - 1 - k0;     // index of the segment's last sample in s[]
+#pragma unroll
+    for (int i = LMAX - 1; i >= 0; --i)
+      if (i <= last) {
+        if (at_end && i == last) {
+          const double below = (i >= 1) ? s[i >= 1 ? i - 1 : 0] : line[(n - 2) * STRIDE];   // still the causal value
+          st = (z / (z * z - 1.0)) * (s[i] + z * below);
+        } else {
+          st = fma(z, st, -z * s[i]);
+        }
+        line[(k0 + i) * STRIDE] = st;
+      }
+  }
+}
+
 // lines along a strided axis.  grid = (ceil(n_cols / L), n_outer), block = 256, tile [n][L],
 // 256 / L segments per line
 template <typename TIn, typename TOut, int L>
@@ -539,8 +607,11 @@ constexpr int kPipeStages = 2;
 // lines along a strided axis (z or y): tile = [n samples] x [L columns]; tiles are numbered
 // outer * x_tiles + x_tile.  float32 in, float32 out.  block = THREADS, dynamic smem =
 // n * L * (4 * kPipeStages + 8) bytes.
+constexpr int kRegSeg = 32;    // longest segment a thread keeps in registers
+constexpr int kRegHorizon = 20;
+
 template <int L, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 cols_pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, int n_outer, ColStrides S) {
   extern __shared__ __align__(16) uint8_t pipe_smem[];
   constexpr int kSegs = THREADS / L;
@@ -591,7 +662,7 @@ cols_pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int n, i
     const int xt = (int)(tile % x_tiles);
     const long long o = tile / x_tiles;
     const int col0 = xt * L, ncol = min(L, n_cols - col0);
-    iir_segment(work + j, n, L, k0, k1, j < ncol && k0 < k1);
+    iir_segment_reg<kRegSeg, kRegHorizon, L>(work + j, n, k0, k1, j < ncol && k0 < k1);
     __syncthreads();
     float* q = out + o * S.outer_out + col0;
     if (out16 && ncol == L) {
@@ -618,7 +689,7 @@ cols_pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int n, i
 // the SM is the x-RESAMPLED float64 volume [rows][out_pitch], so the march that follows only interpolates
 // along y and z.  dynamic smem = L * (n | 1) * 8 + kPipeStages * L * in_pitch * 4 bytes.
 template <int L, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 rows_pipe_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* __restrict__ out, int64_t out_pitch,
                         int n, int nx, int64_t n_rows, const Tap* __restrict__ tx) {
   extern __shared__ __align__(16) uint8_t pipe_smem[];
@@ -659,7 +730,7 @@ rows_pipe_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* 
     for (int r = threadIdx.x >> 5; r < nrow; r += THREADS / 32)
       for (int k = threadIdx.x & 31; k < n; k += 32) work[r * pitch + k] = (double)st[r * sp + k] * kGain;
     __syncthreads();
-    iir_segment(work + r_seg * pitch, n, 1, k0, k1, r_seg < nrow && k0 < k1);
+    iir_segment_reg<kRegSeg, kRegHorizon, 1>(work + r_seg * pitch, n, k0, k1, r_seg < nrow && k0 < k1);
     __syncthreads();
     // a thread owns output columns x, x + THREADS, ...: its taps stay in registers while it walks the rows
     for (int x = threadIdx.x; x < nx; x += THREADS) {
@@ -1131,6 +1202,7 @@ static size_t rows_pipe_smem(int n, int L) {
 
 static bool fast_path_ok(int src_nz_local, int sy, int sx, int ny, int nx) {
   if (g_force_generic || getenv("MICA_NO_TMA") || getenv("MICA_RESAMPLE_OLD")) return false;
+  if (src_nz_local > 1760 || sy > 1760 || sx > 1760) return false;   // 64 segments x kRegSeg samples, tile in smem
   if (src_nz_local < kMinSegLine || sy < kMinSegLine || sx < kMinSegLine) return false;   // segment-parallel sweeps
   if (cols_pipe_smem(src_nz_local, 8) > kPipeSmemMax || cols_pipe_smem(sy, 8) > kPipeSmemMax ||
       rows_pipe_smem(sx, 8) > kPipeSmemMax)
