@@ -599,54 +599,68 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 constexpr int kColH = 16;
 constexpr int kColLen = 26;      // longest segment (registers: kColLen + kColH causal values)
 
+// One segment: samples [k0, k0 + kColLen) of the column at p (element stride line_in), window
+// [k0 - H, k0 + kColLen + H).  EDGE = the window leaves [0, n): indices are mirrored (SciPy's boundary rule;
+// running the recursions over the mirror image replaces the closed-form end initialisation up to
+// |pole|^H).  Interior windows walk the column with pointer increments only.
+template <bool EDGE>
+__device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, float* __restrict__ q, int64_t line_in,
+                                                 int64_t line_out, int n, int k0, int k1) {
+  constexpr int H = kColH, W = kColLen + 2 * kColH;
+  const double z = kPole;
+  float x[W];
+  if (EDGE) {
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      int idx = k0 - H + i;
+      idx = idx < 0 ? -idx : idx;
+      idx = idx > n - 1 ? 2 * (n - 1) - idx : idx;
+      idx = idx < 0 ? 0 : idx;                    // (only for lines shorter than the window)
+      x[i] = __ldg(p + (int64_t)idx * line_in);
+    }
+  } else {
+    const float* r = p + (int64_t)(k0 - H) * line_in;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+      x[i] = __ldg(r);
+      r += line_in;
+    }
+  }
+  double cp[W - H];                               // causal values of samples k0 .. k0 + kColLen + H - 1
+  double st = 0.0;
+#pragma unroll
+  for (int i = 0; i < H; ++i) st = fma(z, st, (double)x[i]);
+#pragma unroll
+  for (int i = H; i < W; ++i) {
+    st = fma(z, st, (double)x[i]);
+    cp[i - H] = st;
+  }
+  const double scale = -z * kGain;                // output = gain * c = gain * (-z) * d
+  double d = 0.0;
+#pragma unroll
+  for (int i = W - H - 1; i >= kColLen; --i) d = fma(z, d, cp[i]);
+  float* o = q + (int64_t)(k0 + kColLen - 1) * line_out;
+#pragma unroll
+  for (int i = kColLen - 1; i >= 0; --i) {
+    d = fma(z, d, cp[i]);
+    if (k0 + i < k1) *o = (float)(d * scale);
+    o -= line_out;
+  }
+}
+
 template <int L, int THREADS>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 cols_reg_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, ColStrides S, int len) {
-  constexpr int H = kColH, M = kColLen + kColH;
-  const double z = kPole;
   const int j = threadIdx.x & (L - 1), seg = threadIdx.x / L;
   const int col0 = blockIdx.x * L;
   const int k0 = seg * len, k1 = min(n, k0 + len);
   if (col0 + j >= n_cols || k0 >= k1) return;
   const float* p = in + (int64_t)blockIdx.y * S.outer_in + col0 + j;
   float* q = out + (int64_t)blockIdx.y * S.outer_out + col0 + j;
-  const int kend = min(n, k1 + H);            // causal values are needed up to here
-  // raw samples: warm-up (mirrored below 0) and the M-long window; all loads are independent
-  float xw[H], xs[M];
-#pragma unroll
-  for (int m = 0; m < H; ++m) {
-    int idx = k0 - 1 - m;
-    idx = idx < 0 ? -idx : idx;
-    xw[m] = __ldg(p + (int64_t)idx * S.line_in);
-  }
-#pragma unroll
-  for (int i = 0; i < M; ++i) xs[i] = (k0 + i < kend) ? __ldg(p + (int64_t)(k0 + i) * S.line_in) : 0.f;
-  double st = 0.0;
-#pragma unroll
-  for (int m = H - 1; m >= 0; --m) st = fma(z, st, (double)xw[m]);
-  const double before = st;                   // causal value of sample k0 - 1
-  double cp[M];
-#pragma unroll
-  for (int i = 0; i < M; ++i) {
-    st = fma(z, st, (double)xs[i]);
-    cp[i] = st;
-  }
-  // anticausal sweep in the d form; the exact end initialisation c[n-1] = z/(z^2-1) (c+[n-1] + z c+[n-2])
-  // replaces the warm-up where the line ends inside the window
-  const double kEnd = -1.0 / (z * z - 1.0);   // c[n-1] / (-z)
-  const double scale = -z * kGain;            // output = gain * c = gain * (-z) * d
-  double d = 0.0;
-#pragma unroll
-  for (int i = M - 1; i >= 0; --i) {
-    const int k = k0 + i;
-    if (k < kend) {
-      if (k == n - 1)
-        d = kEnd * (cp[i] + z * (i >= 1 ? cp[i >= 1 ? i - 1 : 0] : before));
-      else
-        d = fma(z, d, cp[i]);
-      if (k < k1) q[(int64_t)k * S.line_out] = (float)(d * scale);
-    }
-  }
+  if (k0 - kColH >= 0 && k0 + kColLen + kColH <= n)
+    cols_reg_segment<false>(p, q, S.line_in, S.line_out, n, k0, k1);
+  else
+    cols_reg_segment<true>(p, q, S.line_in, S.line_out, n, k0, k1);
 }
 
 // ------------------------------------------------- cp.async-pipelined prefilter passes (fast path)
