@@ -70,8 +70,8 @@ def parse_args():
     ap.add_argument('--no-config5', action='store_true', help='skip the config5 block (configs[4], real MICA)')
     ap.add_argument('--no-dropin', action='store_true', help='skip e2e_dropin')
     ap.add_argument('--config5-cubes', type=int, default=-1,
-                    help='cubes of the 512^3 map pushed through MICA (-1 = all 1331 on 8 GPUs, a bounded subset '
-                         'below: the model costs ~7.4 TFLOP per cube)')
+                    help='cubes of the 512^3 map pushed through MICA (-1 = all 1331; the model costs ~7.4 TFLOP '
+                         'per cube, ~26 ms on a B200)')
     ap.add_argument('--maps-in-flight', type=int, default=0,
                     help='also time K steps with this many maps in flight (one pipeline + stream each); 0 = skip')
     ap.add_argument('--cpu-kind', default='as_is', choices=['as_is', 'port'],
@@ -504,12 +504,9 @@ def config5(ctx):
     bb_ch, aa_ch = channel_codes(st['atom_names'], st['res_names'])
     atoms = tuple(torch.from_numpy(a).to(dev) for a in (st['coords'], bb_ch, aa_ch))
     n_all = 11 ** 3
-    # which cubes: all of them on 8 GPUs (the config as named); below that a bounded subset so that the
-    # default run still ends within minutes -- every 11th cube column (j, k) = 11 cubes spanning all of x
-    if args.config5_cubes < 0:
-        n_cubes = n_all if world >= 8 else 44 * world
-    else:
-        n_cubes = min(n_all, args.config5_cubes)
+    # which cubes: all 1331 (measured: ~26 ms of convolutions per cube on a B200 with TF32 convolutions, i.e.
+    # ~35 s on one GPU, ~4.5 s on eight); --config5-cubes bounds the run to whole x-columns of cubes
+    n_cubes = n_all if args.config5_cubes < 0 else min(n_all, args.config5_cubes)
     ijk_all = np.stack(np.meshgrid(*[np.arange(11)] * 3, indexing='ij'), -1).reshape(-1, 3)
 
     def subset(n):
