@@ -582,7 +582,11 @@ def config5(ctx):
         'stitch': 'ops.postproc_stitch_peer: cores stored into the owning rank\'s exported volume block '
                   '(local or NVLink peer memory), no NCCL on the data path',
     }
-    # ---- parity: the same cubes on ONE GPU, on a small subset whose x-columns touch every owner's range
+    # ---- parity: the same cubes on ONE GPU, on a small subset whose x-columns touch every owner's range.
+    # One cube per model call on both sides: with TF32 convolutions the logits of a cube depend on the batch
+    # it is convolved in (cuDNN picks its algorithm per shape; measured 6e-4 on the probabilities between a
+    # batch of 8 and a batch of 3), so only equal batches isolate what is being checked -- the dataflow.
+    kw = dict(model_batch=1, d8='split')
     par_sel = subset(22) if sel is None or len(sel) > 22 else sel
     pipe_n = BalancedCubePipeline(dev, rank, world, gs, pad, batch_cubes=22, group=grp, cube_subset=par_sel,
                                   _peer_volumes=pipe.peer_volumes)
@@ -608,9 +612,10 @@ def config5(ctx):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     block['parity'] = {'against': f'the same {len(par_sel)} cubes through the same model on ONE GPU (every rank checks '
                                   'its own x range)', 'max_abs_all_ranks': float(t[0]), 'argmax_mismatch_frac_max': float(t[1]),
-                       'ok': bool(float(t[0]) <= 1e-4 and float(t[1]) <= 1e-3),
-                       'tolerance': 'probabilities <= 1e-4 (cuDNN may pick another algorithm for another batch '
-                                    'composition); argmax mismatches <= 1e-3 of the voxels'}
+                       'ok': bool(float(t[0]) <= 1e-5 and float(t[1]) <= 1e-5),
+                       'model_batch': 1,
+                       'tolerance': 'probabilities <= 1e-5; argmax mismatches <= 1e-5 of the voxels (same cube, same '
+                                    'model call shape on both sides)'}
     if pipe.peer_volumes is not None:
         pipe.peer_volumes.close()
     del pipe, pipe_n, single, v_n, v_1, model
