@@ -77,7 +77,10 @@ def test_config1_200_map_whole_path_against_the_oracle(cuda):
             orc.stitch(pred, meta[c0:c0 + n], shp, name, 8, volume=want[name])
     for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
         assert np.abs(vols.as_dict()[k].cpu().numpy() - want[k]).max() <= 1e-5, k
-    assert (vols.amino_acid_prediction.cpu().numpy() == want['amino_acid_prediction']).mean() > 0.9999
+    top2 = np.sort(want['amino_acid_probability'], axis=0)[-2:]
+    clear = (top2[1] - top2[0]) > 4e-6                             # equal wherever the top-2 gap is not rounding
+    assert np.array_equal(vols.amino_acid_prediction.cpu().numpy()[clear], want['amino_acid_prediction'][clear])
+    assert clear.mean() > 0.999
 
 
 # ----------------------------------------------------------------------- config 2: 400^3 -> 480^3
@@ -110,6 +113,36 @@ def test_config2_long_lines_match_scipy(cuda):
     want = orc.resample(src, voxel)
     got = ops.resample(torch.from_numpy(src).to(cuda), want.shape).cpu().numpy()
     assert np.abs(got - want).max() <= 2e-6 * float(np.abs(want).max())
+
+
+def test_fast_path_all_axes_match_scipy(cuda):
+    """Every axis >= 96 samples: float32 z / y prefilter passes (register-only), fused x prefilter +
+    interpolation, TMA-fed y/z march -- against SciPy, incl. an odd row length (no 16-byte aligned rows)
+    and anisotropic zoom."""
+    rng = np.random.default_rng(17)
+    for shape, voxel in (((112, 130, 141), (1.2, 1.2, 1.2)), ((100, 97, 128), (1.06, 1.3, 0.9))):
+        src = rng.normal(size=shape).astype(np.float32)
+        src[10:20, 30:40, 50:60] += 5.0
+        voxel = tuple(np.float32(v) for v in voxel)
+        want = orc.resample(src, voxel)
+        got = ops.resample(torch.from_numpy(src).to(cuda), want.shape).cpu().numpy()
+        assert np.abs(got - want).max() <= 2e-6 * float(np.abs(want).max()), shape
+
+
+def test_config2_full_size_resample_matches_scipy(cuda):
+    """The whole 400^3 -> 480^3 map of BASELINE configs[1] against scipy.ndimage.zoom (about a minute of
+    CPU, once), and the normalised result against the oracle on the [0,1] scale (north_star: 1e-5)."""
+    src = synthetic.synthetic_map((400, 400, 400), voxel=1.2, seed=2022)
+    voxel = (np.float32(1.2),) * 3
+    want = orc.resample(src, voxel)
+    assert want.shape == (480, 480, 480)
+    d = ops.resample(torch.from_numpy(src).to(cuda), want.shape)
+    err = float(np.abs(d.cpu().numpy() - want).max())
+    assert err <= 2e-6 * float(np.abs(want).max()), err
+    o_norm, _, _ = orc.normalize(want)
+    norm, st = ops.normalize(d)
+    assert st.result()[3] == 0
+    assert float(np.abs(norm.cpu().numpy() - o_norm).max()) <= 1e-5
 
 
 def test_config2_order_statistics_of_110M_voxels_are_numpy_exact(cuda, map400):

@@ -59,6 +59,14 @@ def main():
             y = torch.empty_like(res)
             med, best = timeit(lambda: st.apply(res, y))
             print(f'normalize_apply {med:8.3f} ms (best {best:.3f})  {8 * n / med / 1e6:8.1f} GB/s  frac {8 * n / med / 1e6 / peak:.3f}')
+    if 'writepeak' in stages:
+        buf = torch.empty(1 << 31, dtype=torch.uint8, device=dev)          # 2 GiB
+        other = torch.empty_like(buf)
+        med, best = timeit(lambda: buf.zero_())
+        print(f'memset 2 GiB    {med:8.3f} ms (best {best:.3f})  {buf.numel() / med / 1e6:8.1f} GB/s written')
+        med, best = timeit(lambda: other.copy_(buf))
+        print(f'copy 2 GiB      {med:8.3f} ms (best {best:.3f})  {2 * buf.numel() / med / 1e6:8.1f} GB/s read+write')
+        del buf, other
     gs, pad, B = args.grid_size, args.padding, args.batch
     W = gs + 2 * pad
     cs = ops.cube_space_shape(res.shape)
@@ -70,7 +78,7 @@ def main():
         nb = len(ijk) * 4 * (gs ** 3 + W ** 3)
         print(f'extract map x{len(ijk)} {med:8.3f} ms (best {best:.3f})  {nb / med / 1e6:8.1f} GB/s alg  frac {nb / med / 1e6 / peak:.3f}')
     if 'extract24' in stages:
-        Bc = min(B, 64)
+        Bc = min(B, int(os.environ.get('MICA_BENCH_E24', '64')))
         vol = torch.rand((24,) + tuple(res.shape), device=dev)
         x = torch.empty((Bc, 24, W, W, W), device=dev)
         med, best = timeit(lambda: ops.extract_cubes(vol, ijk[:Bc], gs, pad, out=x))
