@@ -45,6 +45,10 @@ struct SelectState {
   // bins -- a few percent of the map -- so that the four later digit passes do not stream the map again
   long long comp_cap;         // capacity in floats; set once per workspace (mica_select_set_compact), survives init
   unsigned long long comp_count;   // floats appended by the guided pass (> comp_cap = overflow: not usable)
+  // the candidate bins as float thresholds (smallest float of bin cand[0], of bin cand[1] + 1, of bin cand[2]):
+  // the compacting guided pass classifies a voxel with three float compares instead of building its key
+  float thr[3];
+  int guided_compact;         // 1 = digit 0 came from the compacting guided pass (histogram built from the buffer)
 };
 
 constexpr int kCompStage = 160;   // per-warp staging slots of the guided pass (flushed when < 32 are free)
@@ -283,11 +287,12 @@ select_sample_kernel(const float* __restrict__ x, long long n, SelectState* __re
 }
 
 __global__ void __launch_bounds__(512)
-select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
+select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s, int allow_compacting) {
   __shared__ unsigned h[kBins];
   __shared__ unsigned long long lump[2];
   __shared__ float stage_all[16][kCompStage];
   if (s->phase0 != 1 || s->status != MICA_NORM_PENDING) return;
+  if (allow_compacting && s->comp_cap > 0) return;   // select_guided_compact_kernel serves this workspace
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
   if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
   __syncthreads();
@@ -382,6 +387,128 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
   if (threadIdx.x == 0) {
     if (lump[0]) atomicAdd(gh + (a_lo > 0 ? a_lo - 1 : 0), lump[0]);
     if (lump[1]) atomicAdd(gh + (p_lo > 0 ? p_lo - 1 : 0), lump[1]);
+  }
+}
+
+// ---- digit 0, compacting form (workspaces with a compact buffer).  ncu on the kernel above: 66 instructions
+// per voxel, 72 % issue-bound -- every voxel pays for the key transform although ~95 % of them only bump a
+// counter.  Here the candidate bins arrive as three float thresholds (pick step 0): a voxel is classified with
+// three compares, the candidates are only APPENDED to the compact buffer (ballot-ranked staging, as above) and
+// their digit-0 histogram is built afterwards from the buffer (select_hist0_compact_kernel: a few percent of
+// the map).  NaN fails every compare and -0 compares equal to +0, so both take the candidate route, where the
+// key is exact; bins outside the candidate ranges that receive such strays are at or below the lumped bins, so
+// every cumulative count the pick uses stays exact.
+__global__ void __launch_bounds__(512)
+select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
+  __shared__ unsigned long long lump[2];
+  __shared__ float stage_all[16][kCompStage];
+  if (s->phase0 != 1 || s->status != MICA_NORM_PENDING || s->comp_cap <= 0) return;
+  if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
+  __syncthreads();
+  const float lo = s->thr[0], hi = s->thr[1], pt = s->thr[2];
+  float* const comp = comp_buffer(s);
+  const long long comp_cap = s->comp_cap;
+  float* const stage = stage_all[threadIdx.x >> 5];
+  const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
+  int staged = 0;   // warp-uniform
+  unsigned c0 = 0, c1 = 0;
+  auto flush = [&]() {
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(&s->comp_count, (unsigned long long)staged);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    __syncwarp();
+    if ((long long)(base + staged) <= comp_cap)
+      for (int i = lane; i < staged; i += 32) comp[base + i] = stage[i];
+    __syncwarp();
+    staged = 0;
+  };
+  auto classify = [&](float v, bool ok) -> bool {
+    const bool below = v < lo, between = (v >= hi) & (v < pt);
+    c0 += (ok & below) ? 1u : 0u;
+    c1 += (ok & between) ? 1u : 0u;
+    return ok & !(below | between);
+  };
+  auto append = [&](bool cand, float v) {
+    const unsigned m = __ballot_sync(0xffffffffu, cand);
+    if (m == 0u) return;
+    if (cand) stage[staged + __popc(m & lt_mask)] = v;
+    staged += __popc(m);
+    if (staged > kCompStage - 32) flush();
+  };
+  long long head = (4 - (long long)(((uintptr_t)x >> 2) & 3)) & 3;
+  if (head > n) head = n;
+  const float4* x4 = reinterpret_cast<const float4*>(x + head);
+  const long long n4 = (n - head) >> 2;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (blockIdx.x == 0 && threadIdx.x < 32) {   // the < 4 scalars before and after the float4 body
+    const long long n_edge = head + (n - head - n4 * 4);
+    const long long e = threadIdx.x;
+    const bool have = e < n_edge;
+    const long long idx = e < head ? e : head + n4 * 4 + (e - head);
+    const float v = have ? x[idx] : 0.f;
+    append(classify(v, have), v);
+  }
+  const long long n4_pad = (n4 + 31) & ~31LL;
+  for (long long i = tid; i < n4_pad; i += stride) {
+    const bool ok = i < n4;
+    const float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool k0 = classify(v.x, ok), k1 = classify(v.y, ok), k2 = classify(v.z, ok), k3 = classify(v.w, ok);
+    if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
+      append(k0, v.x);
+      append(k1, v.y);
+      append(k2, v.z);
+      append(k3, v.w);
+    }
+  }
+  if (staged > 0) flush();
+  for (int o = 16; o > 0; o >>= 1) {
+    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+  }
+  if (lane == 0) {
+    if (c0) atomicAdd(&lump[0], (unsigned long long)c0);
+    if (c1) atomicAdd(&lump[1], (unsigned long long)c1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* gh = reinterpret_cast<unsigned long long*>(&s->hist[0][0]);
+    const int a_lo = s->cand[0], p_lo = s->cand[2];
+    if (lump[0]) atomicAdd(gh + (a_lo > 0 ? a_lo - 1 : 0), lump[0]);
+    if (lump[1]) atomicAdd(gh + (p_lo > 0 ? p_lo - 1 : 0), lump[1]);
+    s->guided_compact = 1;
+  }
+}
+
+// digit-0 histogram of the compacted candidates (exact keys), added to the lumped counts
+__global__ void __launch_bounds__(512)
+select_hist0_compact_kernel(SelectState* __restrict__ s) {
+  __shared__ unsigned h[kBins];
+  if (s->phase0 != 1 || s->status != MICA_NORM_PENDING || s->comp_cap <= 0) return;
+  const long long n = (long long)s->comp_count;
+  if (n > s->comp_cap) {
+    // overflow: this rank's candidate histogram is incomplete.  Word hist[1][0] (unused while digit 0 is being
+    // found) carries the fact through the multi-GPU histogram sum, so EVERY rank's pick asks for the full pass
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      atomicAdd(reinterpret_cast<unsigned long long*>(&s->hist[1][0]), 1ull);
+    return;
+  }
+  if ((long long)blockIdx.x * blockDim.x >= n) return;
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const float* c = comp_buffer(s);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n_pad = (n + 31) & ~31LL;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_pad; i += stride) {
+    const bool ok = i < n;
+    const unsigned bin = ok ? (f32_key(nan_to_num_f32(c[i])) >> 21) : 0u;
+    warp_hist_add(h, bin, ok);
+  }
+  __syncthreads();
+  unsigned long long* gh = reinterpret_cast<unsigned long long*>(&s->hist[0][0]);
+  for (int i = threadIdx.x; i < kBins; i += blockDim.x) {
+    const unsigned v = h[i];
+    if (v) atomicAdd(gh + i, (unsigned long long)v);
   }
 }
 
@@ -493,6 +620,16 @@ select_pick_kernel(SelectState* s, int t) {
       s->cand[0] = a_lo;
       s->cand[1] = a_hi;
       s->cand[2] = p_lo;
+      // float form of the bin edges; an edge that is not an ordinary float (bin 0, NaN patterns) becomes an
+      // infinity so that the compare it feeds is never true and the voxel takes the exact (key) route
+      auto edge = [](int bin, float fallback) {
+        if (bin <= 0 || bin >= kBins) return fallback;
+        const float f = key_f32((unsigned)bin << 21);
+        return (f == f) ? f : fallback;
+      };
+      s->thr[0] = edge(a_lo, -__int_as_float(0x7f800000));        // below  <=> v <  thr[0]
+      s->thr[1] = edge(a_hi + 1, __int_as_float(0x7f800000));     // between <=> thr[1] <= v < thr[2]
+      s->thr[2] = edge(p_lo, __int_as_float(0x7f800000));
       s->phase0 = 1;
     }
     __syncthreads();
@@ -525,7 +662,11 @@ select_pick_kernel(SelectState* s, int t) {
       // every percentile rank is >= 0.9995 N - 1 (at least half of the voxels are <= the median);
       // the margin covers the float32 virtual index of NumPy 2
       const long long need = (long long)(0.00052 * (double)s->n_total) + 64;
-      const bool med_ok = bucket[0] >= a_lo && bucket[0] <= a_hi && bucket[1] >= a_lo && bucket[1] <= a_hi;
+      const bool overflow = s->comp_cap > 0 && s->comp_count > (unsigned long long)s->comp_cap;
+      // the compacting guided pass builds its histogram from the buffer: an overflow on ANY rank (counted in
+      // hist[1][0], summed with the histograms) leaves it incomplete
+      const bool hist_ok = s->hist[1][0] == 0;
+      const bool med_ok = hist_ok && bucket[0] >= a_lo && bucket[0] <= a_hi && bucket[1] >= a_lo && bucket[1] <= a_hi;
       const bool tail_ok = (p_lo == 0) || tail_count >= need;
       if (!(med_ok && tail_ok)) {
         verdict = 0;
@@ -736,6 +877,8 @@ __global__ void select_init_kernel(SelectState* s, long long n_total) {
     s->cand[2] = 0;
     s->comp_ok = 0;
     s->comp_count = 0ull;
+    s->guided_compact = 0;
+    s->thr[0] = s->thr[1] = s->thr[2] = 0.f;
     s->status = n_total > 0 ? MICA_NORM_PENDING : MICA_NORM_NO_POSITIVE;
     s->n_le_med = 0;
     s->n_pos = 0;
@@ -867,7 +1010,16 @@ extern "C" int mica_select_hist(const float* x, int64_t n_local, void* workspace
     select_sample_kernel<<<(unsigned)(ws < kNumSMs ? (ws > 0 ? ws : 1) : kNumSMs), 512, 0, st>>>(x, n_local, s);
     MICA_LAUNCH_CHECK("select_sample_kernel");
   } else if (step == 1) {
-    select_hist0_guided_kernel<<<grid, 512, 0, st>>>(x, n_local, s);
+    // which form runs is decided on the device (whether the workspace has a compact buffer): the other
+    // kernels return at once.  Small inputs never have one, so they only get the histogramming form.
+    const int compacting = !getenv("MICA_SELECT_OLD_GUIDED");
+    if (compacting && n_local >= (1 << 22)) {
+      select_guided_compact_kernel<<<grid, 512, 0, st>>>(x, n_local, s);
+      MICA_LAUNCH_CHECK("select_guided_compact_kernel");
+      select_hist0_compact_kernel<<<kNumSMs * 2, 512, 0, st>>>(s);
+      MICA_LAUNCH_CHECK("select_hist0_compact_kernel");
+    }
+    select_hist0_guided_kernel<<<grid, 512, 0, st>>>(x, n_local, s, compacting);
     MICA_LAUNCH_CHECK("select_hist0_guided_kernel");
   } else if (step == 2) {
     // full digit-0 histogram: at most kHist0MaxPerWarp elements per warp (16-bit counters), >= two CTAs per SM
