@@ -654,23 +654,35 @@ def e2e_dropin(ctx, src_np, header, st, n_vox, host_volumes, steps):
                 bb, ca, aa = ring[0]
                 return bb[:b], ca[:b], aa[:b]
 
+        phase = {}
+
         def once():
+            t = [time.perf_counter()]
+
+            def lap(name):
+                t.append(time.perf_counter())
+                phase[name] = phase.get(name, 0.0) + (t[-1] - t[-2]) * 1e3
             dp = DataPreprocessor(map_path=map_path, AF3_results=af3_results, quiet=True)
             dp.resample_and_normalize_map()
+            lap('resample_and_normalize_map (MRC read + upload + GPU + status)')
             ok = dp.create_AF3_encodings(pdb_path)
+            lap('create_AF3_encodings (PDB parse + upload + atom bins)')
             gc = GridCreator(quiet=True)
             r1 = gc.create_normalized_map_grids(dp.normalized_map_path, os.path.join(grids, 'normalized_map_grids'),
                                                 args.grid_size, args.padding)
             r2 = gc.create_AF3_encodings_grids(dp.AF3_encodings, os.path.join(grids, 'AF3_encoding_grids'),
                                                args.grid_size, args.padding)
+            lap('GridCreator x2 (index only)')
             pr = CryoEMPredictor(model_path='unused', grids_path=grids, output_path=os.path.join(wd, 'out'),
                                  save_output=False, device=str(ctx.dev), quiet=True, model=RingModel(),
                                  host_volumes=host_volumes, host_pool=pool, super_batch=args.batch_cubes)
             good, vols = pr.run_prediction()
+            lap('CryoEMPredictor.run_prediction (cut + model ring + stitch + D2H)')
             assert ok and r1['success'] and r2['success'] and good, 'drop-in sequence failed'
             return vols, pr
         vols, pr = once()                                   # warm: pinned pool, buffers
         torch.cuda.synchronize()
+        phase.clear()
         t0 = time.perf_counter()
         for _ in range(steps):
             vols, pr = once()
@@ -682,6 +694,7 @@ def e2e_dropin(ctx, src_np, header, st, n_vox, host_volumes, steps):
         return {'value': n_vox / dt / 1e9, 'unit': UNIT, 'ms_per_step': dt * 1e3, 'steps': steps,
                 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                 'model_batch': pr._model_batch(), 'host_volumes': list(host_volumes),
+                'phase_ms_per_step': {k: round(v / steps, 2) for k, v in phase.items()},
                 'timing_stats_last': {k: round(float(v), 4) for k, v in pr.timing_stats.items()},
                 'note': 'the utils/modeler.py:673-734 sequence through mica_b200.{DataPreprocessor, GridCreator, '
                         'CryoEMPredictor}: MRC map + PDB model read from tmpfs, model = logits ring fed in the '

@@ -369,6 +369,15 @@ int mica_contour_threshold_f32(const float* in, float* out, int64_t n, float lev
 int mica_zero_around_atoms(const float* xyz, int64_t n_atoms, const float origin_xyz[3], const float voxel_xyz[3],
                            double radius, int nz, int ny, int nx, float* map, int* status_oob, mica_stream_t stream);
 
+/* ------------------------------------------- host I/O helper (no device work)
+ * Fixed-column PDB reader standing where Bio.PDB.PDBParser stands (utils/preprocessing.py:269,275-298).
+ * Per ATOM (and optionally HETATM) record: xyz [n,3] float32 (float(text) rounded to float32),
+ * fields [n,16] uint8 (0-3 atom name cols 13-16, 4 altloc, 5-7 residue name, 8 chain, 9-13 resSeq+iCode,
+ * 14 = HETATM flag), occupancy [n], model [n] (MODEL records seen before).  Returns the record count (only
+ * the first `capacity` are written; capacity 0 counts), negative MICA_ERR_* on an unparsable coordinate. */
+int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_hetatm, int64_t capacity, float* xyz,
+                       uint8_t* fields, float* occupancy, int32_t* model);
+
 #ifdef __cplusplus
 }
 #endif

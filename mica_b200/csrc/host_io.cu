@@ -1,0 +1,117 @@
+// Host-side text munging of the file formats around the hot path: the fixed-column
+// PDB reader that stands where Bio.PDB.PDBParser stands in the reference (utils/preprocessing.py:269,
+// 275-298).  No device code: it lives in the library because a 160 k-atom docked model costs ~40 ms to
+// parse with NumPy and ~3 ms here, and the drop-in's end-to-end time is made of such milliseconds.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace {
+
+// value of a numeric PDB field exactly as Python's float(text) gives it.  Fast path (Clinger): a decimal
+// with <= 15 significant digits and <= 22 fraction digits is mantissa / 10^k with both exactly
+// representable, so one IEEE division is the correctly rounded result.  Anything else goes to strtod.
+bool parse_field(const char* p, int width, double* out) {
+  int i = 0, e = width;
+  while (i < e && (p[i] == ' ' || p[i] == '\t')) ++i;
+  while (e > i && (p[e - 1] == ' ' || p[e - 1] == '\t' || p[e - 1] == '\r')) --e;
+  if (i >= e) return false;
+  bool neg = false;
+  int j = i;
+  if (p[j] == '-' || p[j] == '+') {
+    neg = p[j] == '-';
+    ++j;
+  }
+  unsigned long long mant = 0;
+  int digits = 0, frac = 0;
+  bool seen_point = false, simple = j < e;
+  for (int k = j; k < e; ++k) {
+    const char c = p[k];
+    if (c >= '0' && c <= '9') {
+      mant = mant * 10ull + (unsigned long long)(c - '0');
+      ++digits;
+      if (seen_point) ++frac;
+    } else if (c == '.' && !seen_point) {
+      seen_point = true;
+    } else {
+      simple = false;
+      break;
+    }
+  }
+  if (simple && digits > 0 && digits <= 15 && frac <= 22) {
+    static const double p10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                   1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+    const double v = (double)mant / p10[frac];
+    *out = neg ? -v : v;
+    return true;
+  }
+  char buf[64];
+  const int n = e - i;
+  if (n <= 0 || n >= (int)sizeof(buf)) return false;
+  memcpy(buf, p + i, (size_t)n);
+  buf[n] = 0;
+  char* end = nullptr;
+  const double v = strtod(buf, &end);
+  if (end != buf + n) return false;
+  *out = v;
+  return true;
+}
+
+}  // namespace
+
+// Parses the ATOM (and, with_hetatm != 0, HETATM) records of a PDB text.  Per record r:
+//   xyz[3 r ..]      columns 31-38 / 39-46 / 47-54 as float32 (float(text) rounded to float32, as Bio.PDB stores them)
+//   fields[16 r ..]  0-3 atom name (cols 13-16, with its spacing), 4 altloc (col 17), 5-7 residue name
+//                    (cols 18-20), 8 chain (col 22), 9-13 resSeq + iCode (cols 23-27), 14 = 1 for HETATM, 15 = 0
+//   occupancy[r]     columns 55-60 (0 when blank), model[r] = number of MODEL records seen before it
+// Returns the number of records (at most `capacity` are written; call with capacity 0 to count), or a
+// negative MICA_ERR_* when a coordinate field cannot be parsed.
+extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_hetatm, int64_t capacity, float* xyz,
+                                  uint8_t* fields, float* occupancy, int32_t* model) {
+  if (!text || nbytes < 0) return mica::set_error(MICA_ERR_INVALID, "null PDB text");
+  int64_t n = 0;
+  int32_t n_model = 0;
+  const char* p = text;
+  const char* const end = text + nbytes;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    const int64_t len = le - p;
+    if (len >= 5 && memcmp(p, "MODEL", 5) == 0) {
+      ++n_model;
+    } else if (len >= 6 && (memcmp(p, "ATOM  ", 6) == 0 || (with_hetatm && memcmp(p, "HETATM", 6) == 0))) {
+      if (n < capacity) {
+        char line[61];
+        const int m = len < 60 ? (int)len : 60;
+        memcpy(line, p, (size_t)m);
+        for (int i = m; i < 60; ++i) line[i] = ' ';
+        for (int i = 0; i < 60; ++i)
+          if (line[i] == '\r') line[i] = ' ';
+        double v[3];
+        for (int a = 0; a < 3; ++a)
+          if (!parse_field(line + 30 + 8 * a, 8, &v[a]))
+            return mica::set_error(MICA_ERR_INVALID, "PDB record %lld: cannot parse coordinate %d", (long long)n, a);
+        xyz[3 * n + 0] = (float)v[0];
+        xyz[3 * n + 1] = (float)v[1];
+        xyz[3 * n + 2] = (float)v[2];
+        uint8_t* f = fields + 16 * n;
+        memcpy(f + 0, line + 12, 4);
+        f[4] = (uint8_t)line[16];
+        memcpy(f + 5, line + 17, 3);
+        f[8] = (uint8_t)line[21];
+        memcpy(f + 9, line + 22, 5);
+        f[14] = (p[0] == 'H') ? 1 : 0;
+        f[15] = 0;
+        double occ = 0.0;
+        if (occupancy) occupancy[n] = parse_field(line + 54, 6, &occ) ? (float)occ : 0.f;
+        if (model) model[n] = n_model;
+      }
+      ++n;
+    }
+    if (!nl) break;
+    p = nl + 1;
+  }
+  return n;
+}

@@ -422,6 +422,46 @@ def postproc_stitch(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: t
     return vols
 
 
+class StitchCall:
+    """``postproc_stitch`` bound to one set of volumes and one geometry: everything that does not change from
+    batch to batch (volume pointers, box, shapes) is converted to ctypes once, so the per-call host cost is a
+    handful of microseconds -- the drop-in feeds the model in the reference's batches of <= 8 cubes, i.e.
+    hundreds of stitch calls per map.  The caller guarantees CUDA float32 contiguous logits on the volumes'
+    device (checked on the first call and whenever the batch size changes)."""
+
+    def __init__(self, vols: 'StitchedVolumes', grid_size: int = 48, padding: int = 8):
+        self.vols, self.grid_size, self.padding = vols, int(grid_size), int(padding)
+        self.W = self.grid_size + 2 * self.padding
+        X, Y, Z = vols.shape
+        self._fixed = (X, Y, Z, _lib.int3(vols.org), _lib.int3(vols.ext), self.grid_size, self.padding,
+                       _dev(vols.backbone_probability, torch.float32, 'bb_vol'),
+                       _dev(vols.carbon_alpha_probability, torch.float32, 'ca_vol'),
+                       _dev(vols.amino_acid_probability, torch.float32, 'aa_prob_vol'),
+                       _dev(vols.amino_acid_prediction, torch.float32, 'aa_pred_vol'))
+        self._checked_B = -1
+        self._dev_index = vols.device.index
+
+    def __call__(self, bb, ca, aa, ijk):
+        B = ijk.shape[0]
+        if B != self._checked_B:
+            W = self.W
+            for t, c, name in ((bb, 4, 'bb'), (ca, 4, 'ca'), (aa, 21, 'aa')):
+                if tuple(t.shape) != (B, c, W, W, W):
+                    raise _lib.MicaError(f'{name} logits must be [{B},{c},{W},{W},{W}], got {tuple(t.shape)}')
+                _dev(t, torch.float32, name)
+                if t.device != self.vols.device:
+                    raise _lib.MicaError(f'{name} logits live on {t.device}, the volumes on {self.vols.device}')
+            _dev(ijk, torch.int32, 'ijk')
+            self._checked_B = B
+        if torch.cuda.current_device() != self._dev_index:
+            with torch.cuda.device(self._dev_index):
+                return self(bb, ca, aa, ijk)
+        X, Y, Z, org, ext, gs, pad, p_bb, p_ca, p_aap, p_aapred = self._fixed
+        check(lib.mica_postproc_stitch(bb.data_ptr(), ca.data_ptr(), aa.data_ptr(), ijk.data_ptr(), B, X, Y, Z, org,
+                                       ext, gs, pad, p_bb, p_ca, p_aap, p_aapred,
+                                       torch.cuda.current_stream().cuda_stream), 'postproc_stitch')
+
+
 @device_guard
 def postproc_stitch_peer(bb: torch.Tensor, ca: torch.Tensor, aa: torch.Tensor, ijk: torch.Tensor, cube_shape,
                          owner_table: torch.Tensor, x_bounds, grid_size: int = 48, padding: int = 8):

@@ -6,8 +6,8 @@ is ' ' (ATOM records, :279), coordinates as float32 (Bio.PDB stores float32),
 atom name = columns 13-16 stripped, residue name = columns 18-20.  Text munging
 only; the channel mapping mirrors :254-263,180-185,292-298.
 
-The file is parsed column-wise with NumPy (a 160 k-atom docked model takes ~50 ms instead of
-~0.5 s line by line).  Like Bio.PDB's StructureBuilder, one atom per (model, chain, residue id,
+The records are parsed by ``mica_parse_pdb`` in libmica_b200.so (a 160 k-atom docked model: a few ms;
+a column-wise NumPy reader with identical results serves when the library is not built).  Like Bio.PDB's StructureBuilder, one atom per (model, chain, residue id,
 atom name) survives: of alternate locations the one with the highest occupancy (the first of
 equals), and a second record of the same name with a blank altloc is dropped (Bio.PDB warns
 "defined twice" and ignores it).  The survivor sits where the name first appeared, which is
@@ -70,7 +70,7 @@ def _fixed3(txt8):
     return np.where(minus.any(axis=0), -val, val)
 
 
-def _records(path, with_hetatm):
+def _records_numpy(path, with_hetatm):
     """Column-wise parse of the ATOM (and HETATM) records.  Returns a dict of per-record arrays in file
     order after the Bio.PDB de-duplication: cols (uint8 [A,60]), is_het, model, coords float32 [A,3]."""
     with open(path, 'rb') as fh:
@@ -129,26 +129,71 @@ def _records(path, with_hetatm):
         xyz = v.reshape(-1, 3).astype(np.float32)
     else:
         xyz = np.zeros((0, 3), np.float32)
-    # ---- Bio.PDB de-duplication: one atom per (model, chain, het, resseq+icode, full atom name)
     n = len(cols)
-    order = np.arange(n)
+    fields = np.zeros((n, 16), dtype=np.uint8)
+    occ = np.zeros(n, np.float32)
     if n:
-        key = np.zeros((n, 16), dtype=np.uint8)
-        key[:, 0:4] = cols[:, 12:16]                      # atom name with its spacing
-        key[:, 4] = cols[:, 21]                           # chain
-        key[:, 5:10] = cols[:, 22:27]                     # resSeq + iCode
-        key[:, 10] = het
-        key[:, 11:15] = model.astype('<u4').view(np.uint8).reshape(-1, 4)
-        h = key.view('<u8')
+        fields[:, 0:4] = cols[:, 12:16]
+        fields[:, 4] = cols[:, 16]
+        fields[:, 5:8] = cols[:, 17:20]
+        fields[:, 8] = cols[:, 21]
+        fields[:, 9:14] = cols[:, 22:27]
+        fields[:, 14] = het
+        occ_txt = np.char.strip(np.ascontiguousarray(cols[:, 54:60]).view('S6').ravel())
+        occ = np.array([float(t) if t else 0.0 for t in occ_txt], dtype=np.float32)
+    return fields, np.ascontiguousarray(xyz), occ, model.astype(np.int32)
+
+
+def _records_native(path, with_hetatm):
+    """The same four arrays from libmica_b200.so's ``mica_parse_pdb`` (a 160 k-atom model: ~3 ms instead of
+    ~40 ms).  Returns None when the library is not available (then the NumPy reader does the work)."""
+    try:
+        from . import _lib
+    except ImportError:
+        return None
+    import ctypes as C
+    with open(path, 'rb') as fh:
+        data = fh.read()
+    if not data:
+        return np.zeros((0, 16), np.uint8), np.zeros((0, 3), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int32)
+    cap = len(data) // 54 + 1                             # a record needs its 54 columns
+    xyz = np.empty((cap, 3), np.float32)
+    fields = np.empty((cap, 16), np.uint8)
+    occ = np.empty(cap, np.float32)
+    model = np.empty(cap, np.int32)
+    n = _lib.lib.mica_parse_pdb(data, len(data), int(bool(with_hetatm)), cap, xyz.ctypes.data, fields.ctypes.data,
+                                occ.ctypes.data, model.ctypes.data)
+    if n < 0:
+        raise ValueError(f'{path}: {_lib.last_error()}')
+    return fields[:n], xyz[:n], occ[:n], model[:n]
+
+
+def _records(path, with_hetatm, native=True):
+    """The ATOM (and HETATM) records after the Bio.PDB de-duplication, in file order: dict(fields uint8
+    [A,16] -- 0-3 atom name with its spacing, 4 altloc, 5-7 residue name, 8 chain, 9-13 resSeq + iCode,
+    14 HETATM flag --, coords float32 [A,3], model int32 [A])."""
+    got = _records_native(path, with_hetatm) if native else None
+    if got is None:
+        got = _records_numpy(path, with_hetatm)
+        if got is None:
+            return None
+    fields, xyz, occ, model = got
+    n = len(fields)
+    if n:
+        # ---- Bio.PDB de-duplication: one atom per (model, chain, het, resseq+icode, full atom name)
+        key = np.zeros((n, 24), dtype=np.uint8)
+        key[:, 0:4] = fields[:, 0:4]
+        key[:, 4:10] = fields[:, 8:14]                    # chain, resSeq + iCode
+        key[:, 10] = fields[:, 14]
+        key[:, 12:16] = model.astype('<u4').view(np.uint8).reshape(-1, 4)
+        h = key[:, :16].copy().view('<u8')
         hs = np.sort(h[:, 0] * np.uint64(0x9E3779B97F4A7C15) ^ h[:, 1])
         cnt = np.zeros(1, np.int64)
         if len(hs) > 1 and (hs[1:] == hs[:-1]).any():      # (a hash collision only costs the exact check)
-            kv = key.view('S16').ravel()
+            kv = key.view('S24').ravel()
             _, first, inv, cnt = np.unique(kv, return_index=True, return_inverse=True, return_counts=True)
         if (cnt > 1).any():
-            occ_txt = np.char.strip(np.ascontiguousarray(cols[:, 54:60]).view('S6').ravel())
-            occ = np.array([float(t) if t else 0.0 for t in occ_txt]) if n else np.zeros(0)
-            altloc = cols[:, 16]
+            altloc = fields[:, 4]
             winner = first.copy()                         # per group: record whose coordinates survive
             for g in np.flatnonzero(cnt > 1):
                 members = np.flatnonzero(inv == g)
@@ -165,23 +210,19 @@ def _records(path, with_hetatm):
                 winner[g] = best
             keep_pos = np.sort(first)                     # survivors sit where the name first appeared
             src = winner[inv[keep_pos]]
-            cols_out, xyz = cols[keep_pos].copy(), xyz[src]
-            het, model, order = het[keep_pos], model[keep_pos], keep_pos
-            cols = cols_out
-    return dict(cols=cols, het=het, model=model, coords=np.ascontiguousarray(xyz), order=order)
+            fields, xyz, model = fields[keep_pos], xyz[src], model[keep_pos]
+    return dict(fields=fields, coords=np.ascontiguousarray(xyz), model=model)
 
 
 def _residue_index(rec):
     """Number the residues in file order: a new one starts whenever model / chain / record type /
     sequence number / insertion code changes."""
-    cols = rec['cols']
-    n = len(cols)
+    f = rec['fields']
+    n = len(f)
     if n == 0:
         return np.zeros(0, np.int64)
     key = np.zeros((n, 12), dtype=np.uint8)
-    key[:, 0] = cols[:, 21]
-    key[:, 1:6] = cols[:, 22:27]
-    key[:, 6] = rec['het']
+    key[:, 0:7] = f[:, 8:15]                              # chain, resSeq + iCode, HETATM flag
     key[:, 7:11] = rec['model'].astype('<u4').view(np.uint8).reshape(-1, 4)
     kv = key.view('S12').ravel()
     change = np.concatenate(([True], kv[1:] != kv[:-1]))
@@ -189,15 +230,15 @@ def _residue_index(rec):
 
 
 def _names(rec):
-    cols = rec['cols']
-    atom = np.char.strip(np.ascontiguousarray(cols[:, 12:16]).view('S4').ravel())
-    res = np.char.strip(np.ascontiguousarray(cols[:, 17:20]).view('S3').ravel())
+    f = rec['fields']
+    atom = np.char.strip(np.ascontiguousarray(f[:, 0:4]).view('S4').ravel())
+    res = np.char.strip(np.ascontiguousarray(f[:, 5:8]).view('S3').ravel())
     return atom, res
 
 
-def _res_field4(cols):
-    f = np.full((len(cols), 4), 32, np.uint8)
-    f[:, :3] = cols[:, 17:20]
+def _res_field4(fields):
+    f = np.full((len(fields), 4), 32, np.uint8)
+    f[:, :3] = fields[:, 5:8]
     return f
 
 
@@ -205,11 +246,11 @@ def read_pdb_atoms(path):
     """Returns (coords float32 [A,3] x,y,z; bb_ch int8 [A]; aa_ch int8 [A];
     n_residues) for the ATOM records of ``path``."""
     rec = _records(path, with_hetatm=False)
-    if rec is None or len(rec['cols']) == 0:
+    if rec is None or len(rec['fields']) == 0:
         return np.zeros((0, 3), np.float32), np.zeros(0, np.int8), np.zeros(0, np.int8), 0
     ridx = _residue_index(rec)
-    cols = rec['cols']
-    return rec['coords'], _codes_of(cols[:, 12:16], _BB), _codes_of(_res_field4(cols), _AA), int(ridx[-1]) + 1
+    f = rec['fields']
+    return rec['coords'], _codes_of(f[:, 0:4], _BB), _codes_of(_res_field4(f), _AA), int(ridx[-1]) + 1
 
 
 def read_pdb_records(path):
@@ -220,7 +261,7 @@ def read_pdb_records(path):
     ``res_index`` numbers the residues (a new one starts whenever chain / hetero flag /
     sequence number / insertion code changes)."""
     rec = _records(path, with_hetatm=True)
-    if rec is None or len(rec['cols']) == 0:
+    if rec is None or len(rec['fields']) == 0:
         return dict(coords=np.zeros((0, 3), np.float32), atom_names=[], res_names=[],
                     res_index=np.zeros(0, np.int64))
     atom, res = _names(rec)

@@ -391,12 +391,19 @@ class MapPipeline:
             return vols
         want_flags = d8 == 'split' and (model_batch is None or int(model_batch) > 1)
         if stitch_fn is None:
+            bound = ops.StitchCall(vols, self.grid_size, self.padding)
+
             def stitch_fn(bb, ca, aa, ijk, vols_):
-                ops.postproc_stitch(bb, ca, aa, ijk, vols_, self.grid_size, self.padding)
+                bound(bb, ca, aa, ijk)
+        timed = self.timer is not _no_timer
 
         def stitch(bb, ca, aa, ijk):
-            with self.timer('postproc_stitch'):
-                stitch_fn(_f32c(bb), _f32c(ca), _f32c(aa), ijk, vols)
+            bb, ca, aa = _f32c(bb), _f32c(ca), _f32c(aa)
+            if timed:
+                with self.timer('postproc_stitch'):
+                    stitch_fn(bb, ca, aa, ijk, vols)
+            else:
+                stitch_fn(bb, ca, aa, ijk, vols)
 
         def consume(cur, b0, b1):
             flags = None
