@@ -54,9 +54,14 @@ class DeviceVolume:
     ``amino_acid_probability`` is 20 of the 23 output channels and its only consumer in the reference is a
     gather at the picked C-alpha voxels (utils/modeler.py:850)."""
 
+    #: item reads served by device gathers before the volume is downloaded once and for all: an unmodified
+    #: Solver.clustering reads 27 voxels per picked C-alpha one at a time (utils/modeler.py:846-851)
+    GATHERS_BEFORE_DOWNLOAD = 32
+
     def __init__(self, tensor: torch.Tensor):
         self.tensor = tensor
         self._host = None
+        self._gathers = 0
 
     shape = property(lambda self: tuple(self.tensor.shape))
     ndim = property(lambda self: self.tensor.dim())
@@ -76,6 +81,10 @@ class DeviceVolume:
         return a if dtype is None else a.astype(dtype, copy=False)
 
     def __getitem__(self, idx):
+        if self._host is None:
+            self._gathers += 1
+            if self._gathers > self.GATHERS_BEFORE_DOWNLOAD:
+                self.numpy()
         if self._host is not None:
             return self._host[idx]
         dev = self.tensor.device

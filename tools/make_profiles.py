@@ -19,6 +19,7 @@ out_dir, raw = os.path.join(ROOT, 'profiles'), os.path.join(ROOT, 'gpurun_out')
 
 bench = json.load(open(f'{raw}/bench_{tag}.json'))
 B, S = bench['config']['batch_cubes'], 32
+os.makedirs(out_dir, exist_ok=True)
 shutil.copy(f'{raw}/bench_{tag}.json', f'{out_dir}/{prefix}_bench_final.json')
 
 # ---- launch list
@@ -39,7 +40,7 @@ for (_, k), m in per.items():
     a[2] += m.get('dram__bytes_read.sum', 0)
     a[3] += m.get('dram__bytes_write.sum', 0)
 tot = sum(a[1] for k, a in agg.items() if 'mica::' in k)
-lines = [f'# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-variant --no-cpu-baseline --e2e-steps 1` (B200, {prefix}, batch {B})',
+lines = [f'# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-variant --no-cpu-baseline --no-strong --no-config5 --no-dropin --e2e-steps 1` (B200, {prefix}, batch {B})',
          '# metrics: gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum; --clock-control none; first 600 launches',
          '# per-launch times under ncu are serialised and cold-cache: compare SHARES, not absolutes',
          'kernel,launches,total_us,avg_us,share_of_mica_kernel_time,dram_read_MB_per_launch,dram_write_MB_per_launch']
@@ -59,14 +60,15 @@ for b in txt.split('== ')[1:]:
     if key not in seen or d > seen[key][0]:
         seen[key] = (d, b)
 head = ['ncu --set full --clock-control none --import-source on, one launch per kernel (the longest of each), captured from',
-        f'`python bench.py --steps 1 --warmup 0 --no-variant --no-cpu-baseline --e2e-steps 1` on a B200 ({prefix} final state).',
+        f'`python bench.py --steps 1 --warmup 0 --no-variant --no-cpu-baseline --no-strong --no-config5 --no-dropin --e2e-steps 1` on a B200 ({prefix} final state).',
         f'Workload: 400^3 map @ 1.2 A -> 480^3, 3375 cubes at stride 32, {B} cubes per launch, 167 k atoms.',
         'Per-launch figures are isolated (ncu serialises kernels) and partly cold-cache; bench.py times the same kernels live.', '']
 open(f'{out_dir}/{prefix}_ncu_final.txt', 'w').write('\n'.join(head + ['== ' + b.rstrip() + '\n' for _, b in seen.values()]))
 
 # ---- traffic of the dominant kernel
 m = re.search(r'postproc_stitch_kernel.*?gpu__time_duration.sum\s+([\d.]+) us.*?dram__bytes_read.sum\s+([\d.]+) Mbyte.*?'
-              r'dram__bytes_write.sum\s+([\d.]+) Mbyte', seen['postproc_stitch_kernel'][1], re.S)
+              r'dram__bytes_write.sum\s+([\d.]+) Mbyte',
+              next(v for k, v in seen.items() if 'postproc_stitch_kernel' in k)[1], re.S)
 us, rd, wr = (float(v) for v in m.groups())
 alg = B * S ** 3 * 208
 json.dump({'postproc_stitch_kernel': {
