@@ -373,10 +373,13 @@ int mica_zero_around_atoms(const float* xyz, int64_t n_atoms, const float origin
  * Fixed-column PDB reader standing where Bio.PDB.PDBParser stands (utils/preprocessing.py:269,275-298).
  * Per ATOM (and optionally HETATM) record: xyz [n,3] float32 (float(text) rounded to float32),
  * fields [n,16] uint8 (0-3 atom name cols 13-16, 4 altloc, 5-7 residue name, 8 chain, 9-13 resSeq+iCode,
- * 14 = HETATM flag), occupancy [n], model [n] (MODEL records seen before).  Returns the record count (only
+ * 14 = HETATM flag), occupancy [n], model [n] (MODEL records seen before), bb_ch / aa_ch [n] (channel codes of
+ * utils/preprocessing.py:254-263, -1 = none), info[2] = {residues, 1 if an atom identity occurs twice: altlocs}.
+ * Every output but xyz / fields is nullable.  Returns the record count (only
  * the first `capacity` are written; capacity 0 counts), negative MICA_ERR_* on an unparsable coordinate. */
 int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_hetatm, int64_t capacity, float* xyz,
-                       uint8_t* fields, float* occupancy, int32_t* model);
+                       uint8_t* fields, float* occupancy, int32_t* model, int8_t* bb_ch, int8_t* aa_ch,
+                       int64_t* info);
 
 #ifdef __cplusplus
 }

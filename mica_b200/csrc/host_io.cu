@@ -59,6 +59,32 @@ bool parse_field(const char* p, int width, double* out) {
   return true;
 }
 
+// channel of an atom name / residue name (utils/preprocessing.py:254-263): stripped text compared
+int bb_code(const char* f4) {
+  char t[5];
+  int n = 0;
+  for (int i = 0; i < 4; ++i)
+    if (f4[i] != ' ') t[n++] = f4[i];
+  t[n] = 0;
+  if (!strcmp(t, "CA")) return 0;
+  if (!strcmp(t, "N")) return 1;
+  if (!strcmp(t, "C")) return 2;
+  if (!strcmp(t, "O")) return 3;
+  return -1;
+}
+int aa_code(const char* f3) {
+  static const char* kAA[20] = {"ALA", "CYS", "ASP", "GLU", "PHE", "GLY", "HIS", "ILE", "LYS", "LEU",
+                                "MET", "ASN", "PRO", "GLN", "ARG", "SER", "THR", "VAL", "TRP", "TYR"};
+  char t[4];
+  int n = 0;
+  for (int i = 0; i < 3; ++i)
+    if (f3[i] != ' ') t[n++] = f3[i];
+  t[n] = 0;
+  for (int a = 0; a < 20; ++a)
+    if (!strcmp(t, kAA[a])) return 4 + a;
+  return -1;
+}
+
 }  // namespace
 
 // Parses the ATOM (and, with_hetatm != 0, HETATM) records of a PDB text.  Per record r:
@@ -66,13 +92,25 @@ bool parse_field(const char* p, int width, double* out) {
 //   fields[16 r ..]  0-3 atom name (cols 13-16, with its spacing), 4 altloc (col 17), 5-7 residue name
 //                    (cols 18-20), 8 chain (col 22), 9-13 resSeq + iCode (cols 23-27), 14 = 1 for HETATM, 15 = 0
 //   occupancy[r]     columns 55-60 (0 when blank), model[r] = number of MODEL records seen before it
+//   bb_ch[r] / aa_ch[r]  (nullable) backbone channel 0..3 | -1 and amino-acid channel 4..23 | -1
+//   info                 (nullable) [0] residues (runs of equal model / chain / record type / resSeq+iCode),
+//                        [1] = 1 when two records share (model, chain, record type, resSeq+iCode, atom name) --
+//                        alternate locations or a name defined twice: the caller then applies Bio.PDB's rule
 // Returns the number of records (at most `capacity` are written; call with capacity 0 to count), or a
 // negative MICA_ERR_* when a coordinate field cannot be parsed.
 extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_hetatm, int64_t capacity, float* xyz,
-                                  uint8_t* fields, float* occupancy, int32_t* model) {
+                                  uint8_t* fields, float* occupancy, int32_t* model, int8_t* bb_ch, int8_t* aa_ch,
+                                  int64_t* info) {
   if (!text || nbytes < 0) return mica::set_error(MICA_ERR_INVALID, "null PDB text");
-  int64_t n = 0;
+  int64_t n = 0, n_res = 0;
   int32_t n_model = 0;
+  bool dup = false;
+  // open-addressing set of the 16-byte identity keys (two 64-bit words), sized for the record capacity
+  size_t slots = 64;
+  while (slots < (size_t)(capacity > 0 ? capacity : 0) * 2 + 2) slots <<= 1;
+  unsigned long long* set = (info && capacity > 0) ? (unsigned long long*)calloc(slots * 2, sizeof(unsigned long long)) : nullptr;
+  unsigned char last_res[12];
+  memset(last_res, 0xff, sizeof(last_res));
   const char* p = text;
   const char* const end = text + nbytes;
   while (p < end) {
@@ -91,8 +129,10 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
           if (line[i] == '\r') line[i] = ' ';
         double v[3];
         for (int a = 0; a < 3; ++a)
-          if (!parse_field(line + 30 + 8 * a, 8, &v[a]))
+          if (!parse_field(line + 30 + 8 * a, 8, &v[a])) {
+            free(set);
             return mica::set_error(MICA_ERR_INVALID, "PDB record %lld: cannot parse coordinate %d", (long long)n, a);
+          }
         xyz[3 * n + 0] = (float)v[0];
         xyz[3 * n + 1] = (float)v[1];
         xyz[3 * n + 2] = (float)v[2];
@@ -107,11 +147,52 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
         double occ = 0.0;
         if (occupancy) occupancy[n] = parse_field(line + 54, 6, &occ) ? (float)occ : 0.f;
         if (model) model[n] = n_model;
+        if (bb_ch) bb_ch[n] = (int8_t)bb_code(line + 12);
+        if (aa_ch) aa_ch[n] = (int8_t)aa_code(line + 17);
+        unsigned char res[12];
+        memcpy(res, f + 8, 7);               // chain, resSeq + iCode, HETATM flag
+        memcpy(res + 7, &n_model, 4);
+        res[11] = 0;
+        if (memcmp(res, last_res, 12) != 0) {
+          ++n_res;
+          memcpy(last_res, res, 12);
+        }
+        if (set && !dup) {
+          unsigned long long k0, k1;
+          unsigned char key[16];
+          memcpy(key, f, 4);                 // atom name
+          memcpy(key + 4, res, 12);
+          memcpy(&k0, key, 8);
+          memcpy(&k1, key + 8, 8);
+          k1 |= 1ull << 63;                  // never the empty marker (res[11] == 0 keeps this bit free)
+          unsigned long long x = (k0 * 0x9E3779B97F4A7C15ull) ^ (k1 * 0xC2B2AE3D27D4EB4Full);
+          x ^= x >> 32;                      // the low bits of a product only see the low key bits: fold
+          x *= 0xD6E8FEB86659FD93ull;
+          x ^= x >> 29;
+          size_t h = (size_t)x & (slots - 1);
+          while (true) {
+            if (set[2 * h + 1] == 0) {
+              set[2 * h] = k0;
+              set[2 * h + 1] = k1;
+              break;
+            }
+            if (set[2 * h] == k0 && set[2 * h + 1] == k1) {
+              dup = true;
+              break;
+            }
+            h = (h + 1) & (slots - 1);
+          }
+        }
       }
       ++n;
     }
     if (!nl) break;
     p = nl + 1;
+  }
+  free(set);
+  if (info) {
+    info[0] = n_res;
+    info[1] = dup ? 1 : 0;
   }
   return n;
 }

@@ -161,10 +161,13 @@ def _records_native(path, with_hetatm):
     fields = np.empty((cap, 16), np.uint8)
     occ = np.empty(cap, np.float32)
     model = np.empty(cap, np.int32)
+    bb, aa = np.empty(cap, np.int8), np.empty(cap, np.int8)
+    info = np.zeros(2, np.int64)
     n = _lib.lib.mica_parse_pdb(data, len(data), int(bool(with_hetatm)), cap, xyz.ctypes.data, fields.ctypes.data,
-                                occ.ctypes.data, model.ctypes.data)
+                                occ.ctypes.data, model.ctypes.data, bb.ctypes.data, aa.ctypes.data, info.ctypes.data)
     if n < 0:
         raise ValueError(f'{path}: {_lib.last_error()}')
+    _records_native.last = dict(bb=bb[:n], aa=aa[:n], n_res=int(info[0]), dup=bool(info[1]))
     return fields[:n], xyz[:n], occ[:n], model[:n]
 
 
@@ -179,6 +182,10 @@ def _records(path, with_hetatm, native=True):
             return None
     fields, xyz, occ, model = got
     n = len(fields)
+    extras = getattr(_records_native, 'last', None) if native and got is not None else None
+    _records_native.last = None
+    if extras is not None and len(extras['bb']) == n and not extras['dup']:
+        return dict(fields=fields, coords=np.ascontiguousarray(xyz), model=model, native=extras)
     if n:
         # ---- Bio.PDB de-duplication: one atom per (model, chain, het, resseq+icode, full atom name)
         key = np.zeros((n, 24), dtype=np.uint8)
@@ -248,6 +255,9 @@ def read_pdb_atoms(path):
     rec = _records(path, with_hetatm=False)
     if rec is None or len(rec['fields']) == 0:
         return np.zeros((0, 3), np.float32), np.zeros(0, np.int8), np.zeros(0, np.int8), 0
+    fast = rec.get('native')
+    if fast is not None:                                   # no duplicates: the parser's own codes and count stand
+        return rec['coords'], fast['bb'], fast['aa'], fast['n_res']
     ridx = _residue_index(rec)
     f = rec['fields']
     return rec['coords'], _codes_of(f[:, 0:4], _BB), _codes_of(_res_field4(f), _AA), int(ridx[-1]) + 1
