@@ -73,16 +73,33 @@ int bb_code(const char* f4) {
   return -1;
 }
 int aa_code(const char* f3) {
-  static const char* kAA[20] = {"ALA", "CYS", "ASP", "GLU", "PHE", "GLY", "HIS", "ILE", "LYS", "LEU",
-                                "MET", "ASN", "PRO", "GLN", "ARG", "SER", "THR", "VAL", "TRP", "TYR"};
-  char t[4];
-  int n = 0;
-  for (int i = 0; i < 3; ++i)
-    if (f3[i] != ' ') t[n++] = f3[i];
-  t[n] = 0;
-  for (int a = 0; a < 20; ++a)
-    if (!strcmp(t, kAA[a])) return 4 + a;
-  return -1;
+  if (f3[0] == ' ' || f3[1] == ' ' || f3[2] == ' ') return -1;   // the 20 names fill the field
+  const unsigned k = ((unsigned)(unsigned char)f3[0] << 16) | ((unsigned)(unsigned char)f3[1] << 8) | (unsigned char)f3[2];
+#define AA3(a, b, c) ((unsigned)(a) << 16 | (unsigned)(b) << 8 | (unsigned)(c))
+  switch (k) {
+    case AA3('A', 'L', 'A'): return 4;
+    case AA3('C', 'Y', 'S'): return 5;
+    case AA3('A', 'S', 'P'): return 6;
+    case AA3('G', 'L', 'U'): return 7;
+    case AA3('P', 'H', 'E'): return 8;
+    case AA3('G', 'L', 'Y'): return 9;
+    case AA3('H', 'I', 'S'): return 10;
+    case AA3('I', 'L', 'E'): return 11;
+    case AA3('L', 'Y', 'S'): return 12;
+    case AA3('L', 'E', 'U'): return 13;
+    case AA3('M', 'E', 'T'): return 14;
+    case AA3('A', 'S', 'N'): return 15;
+    case AA3('P', 'R', 'O'): return 16;
+    case AA3('G', 'L', 'N'): return 17;
+    case AA3('A', 'R', 'G'): return 18;
+    case AA3('S', 'E', 'R'): return 19;
+    case AA3('T', 'H', 'R'): return 20;
+    case AA3('V', 'A', 'L'): return 21;
+    case AA3('T', 'R', 'P'): return 22;
+    case AA3('T', 'Y', 'R'): return 23;
+    default: return -1;
+  }
+#undef AA3
 }
 
 }  // namespace
@@ -105,10 +122,10 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
   int64_t n = 0, n_res = 0;
   int32_t n_model = 0;
   bool dup = false;
-  // open-addressing set of the 16-byte identity keys (two 64-bit words), sized for the record capacity
-  size_t slots = 64;
-  while (slots < (size_t)(capacity > 0 ? capacity : 0) * 2 + 2) slots <<= 1;
-  unsigned long long* set = (info && capacity > 0) ? (unsigned long long*)calloc(slots * 2, sizeof(unsigned long long)) : nullptr;
+  // atom names of the residue being read: alternate locations and names "defined twice" repeat a name inside
+  // one residue, which is where this looks (a residue id that reappears later in the file is not detected)
+  unsigned names[256];
+  int n_names = 0;
   unsigned char last_res[12];
   memset(last_res, 0xff, sizeof(last_res));
   const char* p = text;
@@ -130,7 +147,6 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
         double v[3];
         for (int a = 0; a < 3; ++a)
           if (!parse_field(line + 30 + 8 * a, 8, &v[a])) {
-            free(set);
             return mica::set_error(MICA_ERR_INVALID, "PDB record %lld: cannot parse coordinate %d", (long long)n, a);
           }
         xyz[3 * n + 0] = (float)v[0];
@@ -156,32 +172,14 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
         if (memcmp(res, last_res, 12) != 0) {
           ++n_res;
           memcpy(last_res, res, 12);
+          n_names = 0;
         }
-        if (set && !dup) {
-          unsigned long long k0, k1;
-          unsigned char key[16];
-          memcpy(key, f, 4);                 // atom name
-          memcpy(key + 4, res, 12);
-          memcpy(&k0, key, 8);
-          memcpy(&k1, key + 8, 8);
-          k1 |= 1ull << 63;                  // never the empty marker (res[11] == 0 keeps this bit free)
-          unsigned long long x = (k0 * 0x9E3779B97F4A7C15ull) ^ (k1 * 0xC2B2AE3D27D4EB4Full);
-          x ^= x >> 32;                      // the low bits of a product only see the low key bits: fold
-          x *= 0xD6E8FEB86659FD93ull;
-          x ^= x >> 29;
-          size_t h = (size_t)x & (slots - 1);
-          while (true) {
-            if (set[2 * h + 1] == 0) {
-              set[2 * h] = k0;
-              set[2 * h + 1] = k1;
-              break;
-            }
-            if (set[2 * h] == k0 && set[2 * h + 1] == k1) {
-              dup = true;
-              break;
-            }
-            h = (h + 1) & (slots - 1);
-          }
+        if (info && !dup) {
+          unsigned nm;
+          memcpy(&nm, f, 4);
+          for (int i = 0; i < n_names; ++i)
+            if (names[i] == nm) dup = true;
+          if (n_names < 256) names[n_names++] = nm;
         }
       }
       ++n;
@@ -189,7 +187,6 @@ extern "C" int64_t mica_parse_pdb(const char* text, int64_t nbytes, int with_het
     if (!nl) break;
     p = nl + 1;
   }
-  free(set);
   if (info) {
     info[0] = n_res;
     info[1] = dup ? 1 : 0;
