@@ -646,13 +646,21 @@ def e2e_dropin(ctx, src_np, header, st, n_vox, host_volumes, steps):
         ring = ctx.ring
 
         class RingModel:
+            """Stand-in for MICA.forward: logits of the first b cubes of the ring (views made once per size)."""
+
+            def __init__(self):
+                self.views = {}
+
             def eval(self):
                 return self
 
             def __call__(self, x, af):
                 b = x.shape[0]
-                bb, ca, aa = ring[0]
-                return bb[:b], ca[:b], aa[:b]
+                v = self.views.get(b)
+                if v is None:
+                    bb, ca, aa = ring[0]
+                    v = self.views[b] = (bb[:b], ca[:b], aa[:b])
+                return v
 
         phase = {}
 
