@@ -31,6 +31,7 @@ sample of the same workload, on the host cores.
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import shutil
@@ -346,14 +347,20 @@ def make_measure(ctx):
         clocks = ClockSampler(ctx.local_rank) if (with_clocks and rank == 0) else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
-        ev0.record()
-        t_host = time.perf_counter()
-        for _ in range(steps):
-            # status words go to pinned memory in stream order and are checked after the loop (finish()):
-            # no host synchronisation between the maps of the stream
-            vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True)
-        ev1.record()
-        t_host = (time.perf_counter() - t_host) / steps * 1e3      # host time spent enqueueing one step
+        hipri = torch.cuda.Stream(dev, priority=-1) if os.environ.get('MICA_BENCH_HIPRI') else None   # experiment knob
+        if hipri is not None:
+            hipri.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(hipri) if hipri is not None else contextlib.nullcontext():
+            ev0.record()
+            t_host = time.perf_counter()
+            for _ in range(steps):
+                # status words go to pinned memory in stream order and are checked after the loop (finish()):
+                # no host synchronisation between the maps of the stream
+                vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True)
+            ev1.record()
+            t_host = (time.perf_counter() - t_host) / steps * 1e3      # host time spent enqueueing one step
+        if hipri is not None:
+            torch.cuda.current_stream().wait_stream(hipri)
         sync()
         pipe.finish()
         ms = ev0.elapsed_time(ev1)
