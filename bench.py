@@ -31,7 +31,6 @@ sample of the same workload, on the host cores.
 from __future__ import annotations
 
 import argparse
-import contextlib
 import json
 import os
 import shutil
@@ -59,7 +58,7 @@ def parse_args():
     ap.add_argument('--voxel', type=float, default=1.2)
     ap.add_argument('--grid-size', type=int, default=32)
     ap.add_argument('--padding', type=int, default=16)
-    ap.add_argument('--batch-cubes', type=int, default=256)
+    ap.add_argument('--batch-cubes', type=int, default=512)
     ap.add_argument('--cpu-edge', type=int, default=0, help='source edge of the CPU sample (0 = auto)')
     ap.add_argument('--e2e-steps', type=int, default=5)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -347,20 +346,14 @@ def make_measure(ctx):
         clocks = ClockSampler(ctx.local_rank) if (with_clocks and rank == 0) else None
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync()
-        hipri = torch.cuda.Stream(dev, priority=-1) if os.environ.get('MICA_BENCH_HIPRI') else None   # experiment knob
-        if hipri is not None:
-            hipri.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(hipri) if hipri is not None else contextlib.nullcontext():
-            ev0.record()
-            t_host = time.perf_counter()
-            for _ in range(steps):
-                # status words go to pinned memory in stream order and are checked after the loop (finish()):
-                # no host synchronisation between the maps of the stream
-                vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True)
-            ev1.record()
-            t_host = (time.perf_counter() - t_host) / steps * 1e3      # host time spent enqueueing one step
-        if hipri is not None:
-            torch.cuda.current_stream().wait_stream(hipri)
+        ev0.record()
+        t_host = time.perf_counter()
+        for _ in range(steps):
+            # status words go to pinned memory in stream order and are checked after the loop (finish()):
+            # no host synchronisation between the maps of the stream
+            vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True)
+        ev1.record()
+        t_host = (time.perf_counter() - t_host) / steps * 1e3      # host time spent enqueueing one step
         sync()
         pipe.finish()
         ms = ev0.elapsed_time(ev1)

@@ -369,6 +369,18 @@ int mica_contour_threshold_f32(const float* in, float* out, int64_t n, float lev
 int mica_zero_around_atoms(const float* xyz, int64_t n_atoms, const float origin_xyz[3], const float voxel_xyz[3],
                            double radius, int nz, int ny, int nx, float* map, int* status_oob, mica_stream_t stream);
 
+/* ------------------------------------------- overlap-weighted stitching (BASELINE.json north_star variant)
+ * NOT the reference's arithmetic (it pastes disjoint cores, utils/predict.py:494-501): every voxel of every window
+ * adds its post-processed probabilities times a separable window weight w1[a] w1[b] w1[c] (window_w1: W = grid_size
+ * + 2 padding floats on the HOST) to num [22][X][Y][Z] (backbone, C-alpha, 20 amino-acid probabilities) and the
+ * weight to wsum [X][Y][Z]; both zero-initialised by the caller, accumulated over any number of calls.
+ * mica_overlap_finalize divides in place and overwrites wsum with amino_acid_prediction (arg-max of the averaged
+ * probabilities).  With the core-indicator window the result equals mica_postproc_stitch bit for bit. */
+int mica_overlap_accumulate(const float* bb, const float* ca, const float* aa, const int32_t* ijk, int n_cubes,
+                            int X, int Y, int Z, int grid_size, int padding, const float* window_w1, float* num,
+                            float* wsum, mica_stream_t stream);
+int mica_overlap_finalize(float* num, float* wsum, int64_t n_voxels, mica_stream_t stream);
+
 /* ------------------------------------------- host I/O helper (no device work)
  * Fixed-column PDB reader standing where Bio.PDB.PDBParser stands (utils/preprocessing.py:269,275-298).
  * Per ATOM (and optionally HETATM) record: xyz [n,3] float32 (float(text) rounded to float32),

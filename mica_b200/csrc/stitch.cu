@@ -129,6 +129,111 @@ postproc_stitch_kernel(StitchParams P, StitchOwners O) {
   }
 }
 
+// ---------------------------------------------------------------- overlap-weighted stitching (north_star variant)
+// NOT the reference's arithmetic: the reference pastes disjoint cores (utils/predict.py:494-501).
+// BASELINE.json's north_star words the stage as "overlap-averaged stitching ... accumulate prediction plus
+// weight volumes in one pass"; this is that mode, offered next to the reference one.  Every voxel of every W^3
+// window contributes its post-processed probabilities times a separable window weight w1[a] w1[b] w1[c] to 22
+// accumulation channels (backbone, C-alpha, 20 amino-acid probabilities) and the weight itself to a weight
+// volume (red.global.add.f32: windows of one batch overlap, so plain stores would race); a second kernel
+// divides and takes the arg-max.  With the window "1 on the core, 0 on the halo" every voxel receives exactly one
+// contribution of weight 1 and the result is bit-identical to postproc_stitch_kernel (tested).  Parity against
+// the reference for any other window is unpinned by construction.
+constexpr int kOverlapMaxW = 128;
+struct OverlapWindow {
+  float w1[kOverlapMaxW];
+};
+
+// grid = (B, W [window plane a] * ceil(W*W / 256)), block = 256
+__global__ void __launch_bounds__(256)
+overlap_accumulate_kernel(StitchParams P, OverlapWindow Wn, float* __restrict__ num /* [22][X][Y][Z] */,
+                          float* __restrict__ wsum /* [X][Y][Z] */) {
+  const int W = P.W;
+  const int chunks = (W * W + 255) >> 8;
+  const int a = blockIdx.y / chunks, b = blockIdx.x;
+  const float wa = Wn.w1[a];
+  if (wa == 0.f) return;
+  const int i = P.ijk[3 * b + 0], j = P.ijk[3 * b + 1], k = P.ijk[3 * b + 2];
+  const int gx = i - P.pad + a;
+  if ((unsigned)gx >= (unsigned)P.X) return;
+  const int e = (blockIdx.y - a * chunks) * 256 + threadIdx.x;
+  if (e >= W * W) return;
+  const int bj = e / W, c = e - bj * W;
+  const int gy = j - P.pad + bj, gz = k - P.pad + c;
+  if ((unsigned)gy >= (unsigned)P.Y || (unsigned)gz >= (unsigned)P.Z) return;
+  const float w = wa * Wn.w1[bj] * Wn.w1[c];
+  if (w == 0.f) return;
+  const int64_t W3 = (int64_t)W * W * W;
+  const float* bb = P.bb + (int64_t)b * 4 * W3;
+  const float* ca = P.ca + (int64_t)b * 4 * W3;
+  const float* aa = P.aa + (int64_t)b * 21 * W3;
+  const int64_t src = ((int64_t)a * W + bj) * W + c;
+  const int64_t vol_n = (int64_t)P.X * P.Y * P.Z;
+  const int64_t dst = ((int64_t)gx * P.Y + gy) * P.Z + gz;
+  const float b0 = ld_stream(bb + src), b2 = ld_stream(bb + 2 * W3 + src), b3 = ld_stream(bb + 3 * W3 + src);
+  const float c0 = ld_stream(ca + src), c2 = ld_stream(ca + 2 * W3 + src), c3 = ld_stream(ca + 3 * W3 + src);
+  float l[20];
+#pragma unroll
+  for (int t = 0; t < 20; ++t) l[t] = ld_stream(aa + (int64_t)(t + 1) * W3 + src);
+  atomicAdd(num + dst, w * softmax3_last(b0, b2, b3));
+  atomicAdd(num + vol_n + dst, w * softmax3_last(c0, c2, c3));
+  float m = l[0];
+#pragma unroll
+  for (int t = 1; t < 20; ++t) m = fmaxf(m, l[t]);
+  float sum = 0.f;
+#pragma unroll
+  for (int t = 0; t < 20; ++t) {
+    l[t] = exp_neg(l[t] - m);
+    sum += l[t];
+  }
+  const float r = __frcp_rn(sum);
+#pragma unroll
+  for (int t = 0; t < 20; ++t) atomicAdd(num + (int64_t)(2 + t) * vol_n + dst, w * (l[t] * r));
+  atomicAdd(wsum + dst, w);
+}
+
+// num / wsum in place; amino_acid_prediction (arg-max of the averaged probabilities, first maximum wins) is
+// written over the weight volume.  Voxels no window reached (wsum == 0) stay 0.
+__global__ void __launch_bounds__(256)
+overlap_finalize_kernel(float* __restrict__ num, float* __restrict__ wsum, int64_t vol_n) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= vol_n) return;
+  const float w = wsum[v];
+  if (!(w > 0.f)) {
+    wsum[v] = 0.f;
+    return;
+  }
+  if (w == 1.0f) {      // a single unit-weight contribution (the core window): keep the value bit for bit
+    float best = num[2 * vol_n + v];
+    int arg = 0;
+#pragma unroll
+    for (int t = 1; t < 20; ++t) {
+      const float p = num[(int64_t)(2 + t) * vol_n + v];
+      if (p > best) {
+        best = p;
+        arg = t;
+      }
+    }
+    wsum[v] = (float)arg;
+    return;
+  }
+  const float r = 1.0f / w;
+  num[v] *= r;
+  num[vol_n + v] *= r;
+  float best = -1.f;
+  int arg = 0;
+#pragma unroll
+  for (int t = 0; t < 20; ++t) {
+    const float p = num[(int64_t)(2 + t) * vol_n + v] * r;
+    num[(int64_t)(2 + t) * vol_n + v] = p;
+    if (p > best) {
+      best = p;
+      arg = t;
+    }
+  }
+  wsum[v] = (float)arg;
+}
+
 // grid = (S, n_ch, B), block = 256: vol[ch, core] = cubes[b, ch, core]
 __global__ void __launch_bounds__(256)
 stitch_cubes_kernel(const float* __restrict__ cubes, int n_ch, const int32_t* __restrict__ ijk, int X, int Y,
@@ -272,5 +377,52 @@ extern "C" int mica_stitch_cubes(const float* cubes, int n_ch, const int32_t* ij
         ext[1], ext[2], grid_size, padding, W, vol);
     MICA_LAUNCH_CHECK("stitch_cubes_kernel");
   }
+  return MICA_OK;
+}
+
+extern "C" int mica_overlap_accumulate(const float* bb, const float* ca, const float* aa, const int32_t* ijk,
+                                       int n_cubes, int X, int Y, int Z, int grid_size, int padding,
+                                       const float* window_w1 /* host, W floats */, float* num, float* wsum,
+                                       mica_stream_t stream) {
+  MICA_REQUIRE(num && wsum && window_w1, "null pointer");
+  MICA_REQUIRE(n_cubes == 0 || (bb && ca && aa && ijk), "null input");
+  MICA_REQUIRE(grid_size > 0 && padding >= 0 && X > 0 && Y > 0 && Z > 0, "bad geometry");
+  const int W = grid_size + 2 * padding;
+  MICA_REQUIRE(W <= kOverlapMaxW, "window of %d voxels exceeds the %d the weight table holds", W, kOverlapMaxW);
+  if (n_cubes <= 0) return MICA_OK;
+  StitchParams P;
+  P.X = X;
+  P.Y = Y;
+  P.Z = Z;
+  P.org[0] = P.org[1] = P.org[2] = 0;
+  P.ext[0] = X;
+  P.ext[1] = Y;
+  P.ext[2] = Z;
+  P.S = grid_size;
+  P.pad = padding;
+  P.W = W;
+  P.bb_vol = P.ca_vol = P.aa_prob_vol = P.aa_pred_vol = nullptr;
+  OverlapWindow Wn;
+  for (int u = 0; u < kOverlapMaxW; ++u) Wn.w1[u] = u < W ? window_w1[u] : 0.f;
+  const int64_t W3 = (int64_t)W * W * W;
+  const int kMaxX = 32768;
+  for (int b0 = 0; b0 < n_cubes; b0 += kMaxX) {
+    const int nb = (n_cubes - b0 < kMaxX) ? n_cubes - b0 : kMaxX;
+    P.bb = bb + (int64_t)b0 * 4 * W3;
+    P.ca = ca + (int64_t)b0 * 4 * W3;
+    P.aa = aa + (int64_t)b0 * 21 * W3;
+    P.ijk = ijk + 3 * (int64_t)b0;
+    const int chunks = (W * W + 255) / 256;
+    overlap_accumulate_kernel<<<dim3(nb, W * chunks), 256, 0, (cudaStream_t)stream>>>(P, Wn, num, wsum);
+    MICA_LAUNCH_CHECK("overlap_accumulate_kernel");
+  }
+  return MICA_OK;
+}
+
+extern "C" int mica_overlap_finalize(float* num, float* wsum, int64_t n_voxels, mica_stream_t stream) {
+  MICA_REQUIRE(num && wsum && n_voxels >= 0, "bad arguments");
+  if (n_voxels == 0) return MICA_OK;
+  overlap_finalize_kernel<<<(unsigned)ceil_div64(n_voxels, 256), 256, 0, (cudaStream_t)stream>>>(num, wsum, n_voxels);
+  MICA_LAUNCH_CHECK("overlap_finalize_kernel");
   return MICA_OK;
 }

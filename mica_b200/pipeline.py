@@ -367,7 +367,7 @@ class MapPipeline:
     # ---------------------------------------------------------------- stage 5 (+model)
     @_on_device
     def predict_and_stitch(self, model_fn, vols: ops.StitchedVolumes | None = None, on_batch=None, *,
-                           model_batch=None, d8='none', order=None, stitch_fn=None):
+                           model_batch=None, d8='none', order=None, stitch_fn=None, overlap_window=None):
         """run_inference + reconstruct_volume (utils/predict.py:307-587) without the
         per-cube files.  ``model_fn(exp_map, af_features) -> (bb, ca, aa)`` logits, enqueued
         on the current stream.  With ``prefetch`` the cubes of batch n+1 are cut on a side
@@ -380,10 +380,20 @@ class MapPipeline:
         its whole-batch zero-AF3 test, D8).  ``order``: a permutation of the cube indices (the reference
         visits cubes in ``glob`` order, utils/predict.py:269); default = the i-major loop order of
         utils/create_grids.py:143-145.  ``stitch_fn(bb, ca, aa, ijk, vols)`` replaces the local
-        softmax/argmax + stitch (multi-GPU: cores owned by another rank go to its volumes)."""
+        softmax/argmax + stitch (multi-GPU: cores owned by another rank go to its volumes).
+        ``overlap_window`` ('uniform' | 'triangle' | 'core' | W weights): the north_star's overlap-weighted
+        stitching instead of the reference's centre-crop paste (``ops.OverlapStitcher``; NOT the reference's
+        arithmetic) -- whole map on one GPU only."""
         if self.normalized is None:
             raise MicaError('no normalised map')
         self.cube_index()
+        overlap = None
+        if overlap_window is not None:
+            if stitch_fn is not None or getattr(self, 'box', None) is not None:
+                raise MicaError('overlap-weighted stitching needs the whole map on one GPU')
+            overlap = ops.OverlapStitcher(self.cube_shape, self.device, self.grid_size, self.padding, overlap_window)
+            stitch_fn = overlap.accumulate
+            vols = overlap                                # only a handle for on_batch; finalised at the end
         if vols is None:
             vols = self._new_volumes()
         self._custom_order = order is not None
@@ -394,7 +404,7 @@ class MapPipeline:
         n = len(self.ijk_host)
         batches = [(b0, min(n, b0 + self.batch_cubes)) for b0 in range(0, n, self.batch_cubes)]
         if not batches:
-            return vols
+            return overlap.finalize() if overlap is not None else vols
         want_flags = d8 == 'split' and (model_batch is None or int(model_batch) > 1)
         if stitch_fn is None:
             bound = ops.StitchCall(vols, self.grid_size, self.padding)
@@ -425,7 +435,7 @@ class MapPipeline:
                 consume(self.extract_batch(b0, b1, want_flags=want_flags), b0, b1)
                 if on_batch is not None:
                     on_batch(vols, b1)
-            return vols
+            return overlap.finalize() if overlap is not None else vols
 
         t_enqueue = time.perf_counter()
         main = torch.cuda.current_stream(self.device)
@@ -456,7 +466,7 @@ class MapPipeline:
                 on_batch(vols, b1)
             cur = nxt
         self.last_loop_enqueue_ms = (time.perf_counter() - t_enqueue) * 1e3     # host side of the batch loop
-        return vols
+        return overlap.finalize() if overlap is not None else vols
 
     @_on_device
     def finish(self):

@@ -373,6 +373,54 @@ def postprocess_and_stitch(bb_logits, ca_logits, aa_logits, meta, orig_shape, pa
     }
 
 
+def overlap_window(kind, grid_size, padding):
+    """1-D window weights of the overlap-weighted stitch (NOT reference behaviour; BASELINE.json north_star
+    variant): 'core' = the reference's crop (1 on the core, 0 on the halo), 'uniform' = plain
+    average over every window that covers a voxel, 'triangle' = linear ramp peaking at the window centre."""
+    W = grid_size + 2 * padding
+    u = np.arange(W, dtype=np.float64)
+    if kind == 'core':
+        w = ((u >= padding) & (u < padding + grid_size)).astype(np.float64)
+    elif kind == 'uniform':
+        w = np.ones(W)
+    elif kind == 'triangle':
+        w = np.minimum(u + 1, W - u) / (W / 2.0)
+    else:
+        raise ValueError(kind)
+    return w.astype(np.float32)
+
+
+def postprocess_and_stitch_overlap(bb_logits, ca_logits, aa_logits, meta, orig_shape, grid_size, padding, w1):
+    """NumPy statement of the overlap-weighted mode: vol = sum_cubes w * prob / sum_cubes w with the separable
+    window w = w1[a] w1[b] w1[c]; amino_acid_prediction = arg-max of the averaged 20 probabilities.  float64
+    accumulation (the kernel adds float32 atomically in arbitrary order: compare with a tolerance)."""
+    bb, ca, aa_prob, _ = postprocess(bb_logits, ca_logits, aa_logits)
+    X, Y, Z = (int(v) for v in orig_shape)
+    W = grid_size + 2 * padding
+    num = np.zeros((22, X, Y, Z), np.float64)
+    den = np.zeros((X, Y, Z), np.float64)
+    w3 = (w1[:, None, None].astype(np.float64) * w1[None, :, None] * w1[None, None, :])
+    for n, row in enumerate(meta):
+        i, j, k = (int(v) for v in row[:3])
+        lo = [i - padding, j - padding, k - padding]
+        sl_v, sl_c = [], []
+        for a, (o, dim) in enumerate(zip(lo, (X, Y, Z))):
+            v0, v1 = max(0, o), min(dim, o + W)
+            sl_v.append(slice(v0, v1))
+            sl_c.append(slice(v0 - o, v1 - o))
+        sv, sc = tuple(sl_v), tuple(sl_c)
+        w = w3[sc]
+        num[(0,) + sv] += w * bb[n][sc]
+        num[(1,) + sv] += w * ca[n][sc]
+        num[(slice(2, 22),) + sv] += w[None] * aa_prob[n][(slice(None),) + sc]
+        den[sv] += w
+    ok = den > 0
+    out = np.where(ok[None], num / np.where(ok, den, 1.0)[None], 0.0).astype(np.float32)
+    pred = np.where(ok, out[2:].argmax(axis=0), 0).astype(np.float32)
+    return {'backbone_probability': out[0], 'carbon_alpha_probability': out[1],
+            'amino_acid_prediction': pred, 'amino_acid_probability': out[2:]}
+
+
 # ----------------------------------------------------------------------------
 # whole path, in memory (what bench.py's CPU arm times)
 # ----------------------------------------------------------------------------

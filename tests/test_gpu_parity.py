@@ -11,6 +11,7 @@ import pytest
 import torch
 
 from mica_b200 import _lib, ops, synthetic
+from mica_b200.pipeline import MapHeader, MapPipeline
 from oracle import mica_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -523,6 +524,58 @@ def _check_stitched(want, got, logits):
 def test_postproc_stitch_vs_oracle(cuda, cube_shape, gs, pad):
     want, got, logits = _stitch_case(cube_shape, gs, pad, cuda)
     _check_stitched(want, got, logits)
+
+
+@pytest.mark.parametrize('cube_shape,gs,pad', [((70, 33, 50), 32, 16), ((52, 20, 12), 48, 8)])
+def test_overlap_weighted_stitch_modes(cuda, cube_shape, gs, pad):
+    """The north_star's overlap-weighted stitching (NOT the reference's arithmetic): with the
+    core-indicator window it must reproduce the reference-mode kernel bit for bit, with the uniform and the
+    triangle window it must equal the NumPy statement sum(w p) / sum(w) -- float32 atomics in arbitrary
+    order against float64 accumulation, so with a tolerance."""
+    want_core, got_core, (bb, ca, aa, meta) = _stitch_case(cube_shape, gs, pad, cuda)
+    d = [dev(a, cuda) for a in (bb, ca, aa)]
+    ijk = dev(np.ascontiguousarray(meta[:, :3], dtype=np.int32), cuda)
+    half = len(meta) // 2                                   # two accumulate calls: batches add up
+    for window in ('core', 'uniform', 'triangle'):
+        st = ops.OverlapStitcher(cube_shape, cuda, gs, pad, window)
+        st.accumulate(d[0][:half], d[1][:half], d[2][:half], ijk[:half])
+        st.accumulate(d[0][half:], d[1][half:], d[2][half:], ijk[half:])
+        got = {k: v.cpu().numpy() for k, v in st.finalize().as_dict().items()}
+        if window == 'core':
+            for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+                assert np.array_equal(got[k], got_core[k]), k       # same softmax, weight 1, one contribution
+            _check_stitched(want_core, got, None)
+            continue
+        w1 = orc.overlap_window(window, gs, pad)
+        assert np.array_equal(w1, ops.overlap_window(window, gs, pad))
+        want = orc.postprocess_and_stitch_overlap(bb, ca, aa, meta, cube_shape, gs, pad, w1)
+        for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+            assert np.abs(got[k] - want[k]).max() <= TOL, (window, k)
+        p = np.sort(want['amino_acid_probability'], axis=0)
+        clear = (p[-1] - p[-2]) > 4e-6
+        assert np.array_equal(got['amino_acid_prediction'][clear], want['amino_acid_prediction'][clear]), window
+        # every voxel of the map is covered by at least one window: probabilities of the 20 classes sum to 1
+        assert np.abs(got['amino_acid_probability'].sum(0) - 1).max() <= 1e-5
+    with pytest.raises(_lib.MicaError):
+        ops.OverlapStitcher(cube_shape, cuda, gs, pad, 'hamming')
+
+
+def test_pipeline_overlap_window_option(cuda):
+    """MapPipeline.predict_and_stitch(overlap_window=...) routes the batches through the OverlapStitcher; 'core'
+    equals the default mode."""
+    src = synthetic.synthetic_map((40, 44, 36), voxel=1.0, seed=9)
+    hdr = MapHeader(voxel_size=(np.float32(1.0),) * 3)
+    pipe = MapPipeline(cuda, 32, 16, batch_cubes=3)
+    assert pipe.resample_and_normalize(dev(src, cuda), hdr)
+    with torch.no_grad():
+        ref = pipe.predict_and_stitch(synthetic.pointwise_model)
+        core = pipe.predict_and_stitch(synthetic.pointwise_model, overlap_window='core')
+        uni = pipe.predict_and_stitch(synthetic.pointwise_model, overlap_window='uniform')
+    for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+        assert torch.equal(core.as_dict()[k], ref.as_dict()[k]), k
+    # a pointwise model gives every window the same value at a voxel: averaging changes nothing but rounding
+    for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
+        assert float((uni.as_dict()[k] - ref.as_dict()[k]).abs().max()) <= 1e-6, k
 
 
 def test_postproc_stitch_golden(cuda, golden_dir):
