@@ -839,6 +839,27 @@ def run_ours(args):
         v48['note'] = ('dense: B(N) = 661 B/voxel of SURVEY 8(d) over the dense-AF3 step time; sparse: the bytes the '
                        'sparse dataflow moves over its step time')
         variant_48_8 = v48
+        # north_star's overlap-weighted stitching (NOT the reference's arithmetic): every voxel of
+        # every 64^3 window is post-processed and accumulated with its weight, then divided
+        po = make_pipe(args.af3_mode)
+        for _ in range(2):
+            po.run(src, header, atoms, model_fn, None, overlap_window='uniform')
+        sync()
+        eo0, eo1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        eo0.record()
+        for _ in range(5):
+            po.run(src, header, atoms, model_fn, None, defer_check=True, overlap_window='uniform')
+        eo1.record()
+        sync()
+        po.finish()
+        ms_o = eo0.elapsed_time(eo1) / 5
+        variant['overlap_weighted_stitch'] = {
+            'window': 'uniform', 'ms_per_step': ms_o, 'value': n_vox / (ms_o * 1e-3) / 1e9, 'unit': UNIT,
+            'note': "BASELINE north_star's wording of the stitch (accumulate prediction x weight and weight volumes, "
+                    'divide); the reference pastes disjoint cores, which is what every other number in this line '
+                    'does.  8x the voxels of the core-only mode go through softmax and 23 float atomics each'}
+        del po
+        torch.cuda.empty_cache()
         vols = pipe.run(src, header, atoms, model_fn, None)
 
     # ---------------- several maps in flight (a stream of maps).  Reported as a variant.
