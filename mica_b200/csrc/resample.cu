@@ -28,6 +28,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mica {
@@ -599,32 +601,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 constexpr int kColH = 16;
 constexpr int kColLen = 26;      // longest segment (registers: kColLen + kColH causal values)
 
-// One segment: samples [k0, k0 + kColLen) of the column at p (element stride line_in), window
-// [k0 - H, k0 + kColLen + H).  EDGE = the window leaves [0, n): indices are mirrored (SciPy's boundary rule;
-// running the recursions over the mirror image replaces the closed-form end initialisation up to
-// |pole|^H).  Interior windows walk the column with pointer increments only.
-template <bool EDGE>
-__device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, float* __restrict__ q, int64_t line_in,
-                                                 int64_t line_out, int n, int k0, int k1) {
+// One segment: samples [k0, k0 + kColLen) of a line, window [k0 - H, k0 + kColLen + H).  `load(idx)` returns
+// sample idx as float, `store(k, value)` takes the finished coefficient of sample k.  EDGE = the window leaves
+// [0, n): indices are mirrored (SciPy's boundary rule; running the recursions over the mirror image replaces the
+// closed-form end initialisation up to |pole|^H).
+template <bool EDGE, typename Load, typename Store>
+__device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k0, int k1) {
   constexpr int H = kColH, W = kColLen + 2 * kColH;
   const double z = kPole;
   float x[W];
-  if (EDGE) {
 #pragma unroll
-    for (int i = 0; i < W; ++i) {
-      int idx = k0 - H + i;
+  for (int i = 0; i < W; ++i) {
+    int idx = k0 - H + i;
+    if (EDGE) {
       idx = idx < 0 ? -idx : idx;
       idx = idx > n - 1 ? 2 * (n - 1) - idx : idx;
       idx = idx < 0 ? 0 : idx;                    // (only for lines shorter than the window)
-      x[i] = __ldg(p + (int64_t)idx * line_in);
     }
-  } else {
-    const float* r = p + (int64_t)(k0 - H) * line_in;
-#pragma unroll
-    for (int i = 0; i < W; ++i) {
-      x[i] = __ldg(r);
-      r += line_in;
-    }
+    x[i] = load(idx);
   }
   double cp[W - H];                               // causal values of samples k0 .. k0 + kColLen + H - 1
   double st = 0.0;
@@ -639,13 +633,18 @@ __device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, fl
   double d = 0.0;
 #pragma unroll
   for (int i = W - H - 1; i >= kColLen; --i) d = fma(z, d, cp[i]);
-  float* o = q + (int64_t)(k0 + kColLen - 1) * line_out;
 #pragma unroll
   for (int i = kColLen - 1; i >= 0; --i) {
     d = fma(z, d, cp[i]);
-    if (k0 + i < k1) *o = (float)(d * scale);
-    o -= line_out;
+    if (k0 + i < k1) store(k0 + i, d * scale);
   }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, float* __restrict__ q, int64_t line_in,
+                                                 int64_t line_out, int n, int k0, int k1) {
+  reg_segment<EDGE>([&](int idx) { return __ldg(p + (int64_t)idx * line_in); },
+                    [&](int k, double v) { q[(int64_t)k * line_out] = (float)v; }, n, k0, k1);
 }
 
 template <int L, int THREADS>
@@ -756,6 +755,72 @@ cols_pipe_kernel(const float* __restrict__ in, float* __restrict__ out, int n, i
       }
     }
     __syncthreads();                                   // work tile and stage sidx are free again
+    sidx = (sidx + 1) % kPipeStages;
+  }
+  cp_async_wait<0>();
+}
+
+// x axis, register form (rows of <= 32 x kColLen samples): as rows_pipe_interp_kernel below, but the sweep is the
+// register-only segment of the column pass -- a thread pulls the 58-sample window of its segment out of the
+// staged float32 row (lanes = the 16 or 32 segments of a row: odd segment lengths keep the banks distinct), runs
+// both recursions in registers and writes its <= 26 coefficients to the float64 work tile once: one barrier
+// before the interpolation instead of five.  dynamic smem = L * (n | 1) * 8 + kPipeStages * L * in_pitch * 4.
+template <int SEGS>
+__global__ void __launch_bounds__(16 * SEGS, 512 / (16 * SEGS))
+rows_reg_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* __restrict__ out, int64_t out_pitch,
+                       int n, int nx, int64_t n_rows, const Tap* __restrict__ tx, int len) {
+  extern __shared__ __align__(16) uint8_t pipe_smem[];
+  constexpr int L = 16, THREADS = 16 * SEGS;
+  const int pitch = n | 1;
+  const int sp = (int)in_pitch;
+  double* work = reinterpret_cast<double*>(pipe_smem);
+  float* stage0 = reinterpret_cast<float*>(pipe_smem + (((size_t)L * pitch * 8 + 15) & ~(size_t)15));
+  const uint32_t stage_a = smem_addr(stage0);
+  const long long n_tiles = (n_rows + L - 1) / L;
+  const int chunks = sp / 4;
+  auto prefetch = [&](long long tile, int sidx) {
+    if (tile < n_tiles) {
+      const int64_t row0 = tile * L;
+      const int nrow = (int)min((int64_t)L, n_rows - row0);
+      const float* g = in + row0 * in_pitch;
+      const uint32_t dst = stage_a + (uint32_t)sidx * (uint32_t)(L * sp * 4);
+      for (int e = threadIdx.x; e < nrow * chunks; e += THREADS) cp_async16(dst + (uint32_t)(e * 16), g + (int64_t)e * 4);
+    }
+    cp_async_commit();
+  };
+  long long tile = blockIdx.x;
+  for (int i = 0; i < kPipeStages - 1; ++i) prefetch(tile + (long long)i * gridDim.x, i);
+  int sidx = 0;
+  const int seg = threadIdx.x % SEGS, r = threadIdx.x / SEGS;
+  const int k0 = seg * len, k1 = min(n, k0 + len);
+  const bool interior = k0 - kColH >= 0 && k0 + kColLen + kColH <= n;
+  for (; tile < n_tiles; tile += gridDim.x) {
+    prefetch(tile + (long long)(kPipeStages - 1) * gridDim.x, (sidx + kPipeStages - 1) % kPipeStages);
+    cp_async_wait<kPipeStages - 1>();
+    __syncthreads();                                   // staged rows visible; the work tile of the last tile is consumed
+    const int64_t row0 = tile * L;
+    const int nrow = (int)min((int64_t)L, n_rows - row0);
+    if (r < nrow && k0 < k1) {
+      const float* srow = stage0 + (size_t)sidx * L * sp + (size_t)r * sp;
+      double* wrow = work + (size_t)r * pitch;
+      auto load = [&](int idx) { return srow[idx]; };
+      auto store = [&](int k, double v) { wrow[k] = v; };
+      if (interior)
+        reg_segment<false>(load, store, n, k0, k1);
+      else
+        reg_segment<true>(load, store, n, k0, k1);
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < nx; x += THREADS) {
+      const Tap T = tx[x];
+      double* o = out + row0 * out_pitch + x;
+#pragma unroll 4
+      for (int rr = 0; rr < nrow; ++rr) {
+        const double* row = work + rr * pitch;
+        o[(int64_t)rr * out_pitch] = T.w[0] * row[T.idx[0]] + T.w[1] * row[T.idx[1]] + T.w[2] * row[T.idx[2]] +
+                                     T.w[3] * row[T.idx[3]];
+      }
+    }
     sidx = (sidx + 1) % kPipeStages;
   }
   cp_async_wait<0>();
@@ -1102,25 +1167,24 @@ march_yz_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ZWin* __rest
   int next_emit = zw[zc].base + 3;
   int sidx = 0;
   uint32_t phase = 0;
-  for (int p = p_start; p <= p_last; ++p) {
+  // The 4-plane window is a ring of registers whose head is a COMPILE-TIME index (the plane loop is unrolled
+  // by four), so a new plane overwrites the oldest slot instead of shifting the window: no register moves.
+  auto step = [&](auto hc, int p) {
+    constexpr int h = decltype(hc)::value;        // slot of plane p; the window, oldest first: h+1, h+2, h+3, h
     mbar_wait(smem_addr(&full[sidx]), phase);
     const uint32_t raw = ring_base + (uint32_t)sidx * kStageBytes;
 #pragma unroll
-    for (int o = 0; o < 2; ++o) {
-      const double vn = wy[o][0] * lds(raw + a_rd[o][0]) + wy[o][1] * lds(raw + a_rd[o][1]) +
-                        wy[o][2] * lds(raw + a_rd[o][2]) + wy[o][3] * lds(raw + a_rd[o][3]);
-      v[o][0] = v[o][1];
-      v[o][1] = v[o][2];
-      v[o][2] = v[o][3];
-      v[o][3] = vn;
-    }
+    for (int o = 0; o < 2; ++o)
+      v[o][h] = wy[o][0] * lds(raw + a_rd[o][0]) + wy[o][1] * lds(raw + a_rd[o][1]) +
+                wy[o][2] * lds(raw + a_rd[o][2]) + wy[o][3] * lds(raw + a_rd[o][3]);
     __syncthreads();   // every thread has read ring stage sidx: it may be refilled
     if (t == 0 && p + kYzStages <= p_last) issue(p + kYzStages, sidx);
     while (zc < z_end && next_emit <= p) {
       const ZWin Wz = zw[zc];
 #pragma unroll
       for (int o = 0; o < 2; ++o) {
-        const double acc = Wz.w[0] * v[o][0] + Wz.w[1] * v[o][1] + Wz.w[2] * v[o][2] + Wz.w[3] * v[o][3];
+        const double acc = Wz.w[0] * v[o][(h + 1) & 3] + Wz.w[1] * v[o][(h + 2) & 3] + Wz.w[2] * v[o][(h + 3) & 3] +
+                           Wz.w[3] * v[o][h];
         if (outok[o]) st_stream(outp[o], (float)acc);
         outp[o] += out_plane;
       }
@@ -1131,7 +1195,21 @@ march_yz_tma_kernel(const __grid_constant__ CUtensorMap tmap, const ZWin* __rest
       sidx = 0;
       phase ^= 1u;
     }
+  };
+  using I0 = std::integral_constant<int, 0>;
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+  using I3 = std::integral_constant<int, 3>;
+  int p = p_start;
+  for (; p + 3 <= p_last; p += 4) {
+    step(I0(), p);
+    step(I1(), p + 1);
+    step(I2(), p + 2);
+    step(I3(), p + 3);
   }
+  if (p <= p_last) step(I0(), p);
+  if (p + 1 <= p_last) step(I1(), p + 1);
+  if (p + 2 <= p_last) step(I2(), p + 2);
 }
 
 __global__ void __launch_bounds__(128)
@@ -1342,9 +1420,30 @@ static int launch_rows_pipe_t(const float* in, int64_t in_pitch, double* out, in
   MICA_LAUNCH_CHECK("rows_pipe_interp_kernel");
   return MICA_OK;
 }
+template <int SEGS>
+static int launch_rows_reg_t(const float* in, int64_t in_pitch, double* out, int64_t out_pitch, int n, int nx,
+                             int64_t n_rows, const Tap* tx, cudaStream_t st) {
+  const size_t smem = rows_pipe_smem(n, 16);
+  MICA_CUDA(cudaFuncSetAttribute(rows_reg_interp_kernel<SEGS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = (int)((size_t)225 * 1024 / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > 512 / (16 * SEGS) ? 512 / (16 * SEGS) : per_sm);
+  const long long tiles = (n_rows + 15) / 16;
+  long long grid = (long long)kNumSMs * per_sm;
+  if (grid > tiles) grid = tiles;
+  int len = (n + SEGS - 1) / SEGS;
+  if (len % 2 == 0 && len < kColLen) ++len;      // odd segment length: the lanes of a row hit distinct banks
+  rows_reg_interp_kernel<SEGS><<<(unsigned)grid, 16 * SEGS, smem, st>>>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, len);
+  MICA_LAUNCH_CHECK("rows_reg_interp_kernel");
+  return MICA_OK;
+}
+
 static int launch_rows_pipe(const float* in, int64_t in_pitch, double* out, int64_t out_pitch, int n, int nx,
                             int64_t n_rows, const Tap* tx, cudaStream_t st) {
   if (n_rows <= 0) return MICA_OK;
+  if (!getenv("MICA_RESAMPLE_NOREG") && rows_pipe_smem(n, 16) <= kPipeSmemMax) {
+    if (n <= 16 * kColLen) return launch_rows_reg_t<16>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
+    if (n <= 32 * kColLen) return launch_rows_reg_t<32>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
+  }
   if (rows_pipe_smem(n, 16) <= 110 * 1024) return launch_rows_pipe_t<16, 256>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
   if (rows_pipe_smem(n, 16) <= kPipeSmemMax) return launch_rows_pipe_t<16, 512>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);
   return launch_rows_pipe_t<8, 512>(in, in_pitch, out, out_pitch, n, nx, n_rows, tx, st);

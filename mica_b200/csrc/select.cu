@@ -662,7 +662,6 @@ select_pick_kernel(SelectState* s, int t) {
       // every percentile rank is >= 0.9995 N - 1 (at least half of the voxels are <= the median);
       // the margin covers the float32 virtual index of NumPy 2
       const long long need = (long long)(0.00052 * (double)s->n_total) + 64;
-      const bool overflow = s->comp_cap > 0 && s->comp_count > (unsigned long long)s->comp_cap;
       // the compacting guided pass builds its histogram from the buffer: an overflow on ANY rank (counted in
       // hist[1][0], summed with the histograms) leaves it incomplete
       const bool hist_ok = s->hist[1][0] == 0;
