@@ -634,17 +634,30 @@ __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k
 #pragma unroll
   for (int i = W - H - 1; i >= kColLen; --i) d = fma(z, d, cp[i]);
 #pragma unroll
-  for (int i = kColLen - 1; i >= 0; --i) {
+  for (int i = kColLen - 1; i >= 0; --i) {     // store is called for every i, downwards (it may walk a pointer)
     d = fma(z, d, cp[i]);
-    if (k0 + i < k1) store(k0 + i, d * scale);
+    store(k0 + i, d * scale, k0 + i < k1);
   }
 }
 
 template <bool EDGE>
 __device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, float* __restrict__ q, int64_t line_in,
                                                  int64_t line_out, int n, int k0, int k1) {
-  reg_segment<EDGE>([&](int idx) { return __ldg(p + (int64_t)idx * line_in); },
-                    [&](int k, double v) { q[(int64_t)k * line_out] = (float)v; }, n, k0, k1);
+  float* o = q + (int64_t)(k0 + kColLen - 1) * line_out;
+  auto store = [&](int, double v, bool on) {
+    if (on) *o = (float)v;
+    o -= line_out;
+  };
+  if (EDGE) {
+    reg_segment<true>([&](int idx) { return __ldg(p + (int64_t)idx * line_in); }, store, n, k0, k1);
+  } else {   // interior windows are read in increasing order: walk the column with pointer increments only
+    const float* r = p + (int64_t)(k0 - kColH) * line_in;
+    reg_segment<false>([&](int) {
+      const float v = __ldg(r);
+      r += line_in;
+      return v;
+    }, store, n, k0, k1);
+  }
 }
 
 template <int L, int THREADS>
@@ -804,7 +817,9 @@ rows_reg_interp_kernel(const float* __restrict__ in, int64_t in_pitch, double* _
       const float* srow = stage0 + (size_t)sidx * L * sp + (size_t)r * sp;
       double* wrow = work + (size_t)r * pitch;
       auto load = [&](int idx) { return srow[idx]; };
-      auto store = [&](int k, double v) { wrow[k] = v; };
+      auto store = [&](int k, double v, bool on) {
+        if (on) wrow[k] = v;
+      };
       if (interior)
         reg_segment<false>(load, store, n, k0, k1);
       else
