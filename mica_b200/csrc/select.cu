@@ -393,47 +393,56 @@ select_hist0_guided_kernel(const float* __restrict__ x, long long n, SelectState
 // ---- digit 0, compacting form (workspaces with a compact buffer).  ncu on the kernel above: 66 instructions
 // per voxel, 72 % issue-bound -- every voxel pays for the key transform although ~95 % of them only bump a
 // counter.  Here the candidate bins arrive as three float thresholds (pick step 0): a voxel is classified with
-// three compares, the candidates are only APPENDED to the compact buffer (ballot-ranked staging, as above) and
+// three compares, the candidates are only APPENDED to the compact buffer (lane-private shared-memory queues,
+// flushed warp-wide) and
 // their digit-0 histogram is built afterwards from the buffer (select_hist0_compact_kernel: a few percent of
 // the map).  NaN fails every compare and -0 compares equal to +0, so both take the candidate route, where the
 // key is exact; bins outside the candidate ranges that receive such strays are at or below the lumped bins, so
 // every cumulative count the pick uses stays exact.
+constexpr int kLaneQueue = 8;     // candidate slots per lane between two warp-wide flushes
+
 __global__ void __launch_bounds__(512)
 select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
   __shared__ unsigned long long lump[2];
-  __shared__ float stage_all[16][kCompStage];
+  __shared__ float queue_all[512 * kLaneQueue];   // [slot][thread]: lane-private queues, conflict-free
   if (s->phase0 != 1 || s->status != MICA_NORM_PENDING || s->comp_cap <= 0) return;
   if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
   __syncthreads();
   const float lo = s->thr[0], hi = s->thr[1], pt = s->thr[2];
   float* const comp = comp_buffer(s);
   const long long comp_cap = s->comp_cap;
-  float* const stage = stage_all[threadIdx.x >> 5];
-  const unsigned lane = threadIdx.x & 31, lt_mask = (1u << lane) - 1u;
-  int staged = 0;   // warp-uniform
+  float* const queue = queue_all + threadIdx.x;    // slot q of this lane: queue[q * 512]
+  const unsigned lane = threadIdx.x & 31;
+  int queued = 0;                                  // this lane's candidates waiting for the next flush
   unsigned c0 = 0, c1 = 0;
+  // A candidate costs its lane one predicated shared store and one add -- no ballot per value.  When some
+  // lane's queue could overflow in the next iteration (>= kLaneQueue - 4 entries) the warp flushes: a shuffle
+  // scan of the 32 counts, one global atomic for the warp, every lane copies its entries to its range.
   auto flush = [&]() {
+    int incl = queued;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int up = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((int)lane >= o) incl += up;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&s->comp_count, (unsigned long long)staged);
+    if (lane == 0) base = atomicAdd(&s->comp_count, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    __syncwarp();
-    if ((long long)(base + staged) <= comp_cap)
-      for (int i = lane; i < staged; i += 32) comp[base + i] = stage[i];
-    __syncwarp();
-    staged = 0;
+    if ((long long)(base + total) <= comp_cap) {
+      const unsigned long long at = base + (unsigned long long)(incl - queued);
+      for (int q = 0; q < queued; ++q) comp[at + q] = queue[q * 512];
+    }
+    queued = 0;
   };
-  auto classify = [&](float v, bool ok) -> bool {
+  auto take = [&](float v, bool ok) {
     const bool below = v < lo, between = (v >= hi) & (v < pt);
     c0 += (ok & below) ? 1u : 0u;
     c1 += (ok & between) ? 1u : 0u;
-    return ok & !(below | between);
-  };
-  auto append = [&](bool cand, float v) {
-    const unsigned m = __ballot_sync(0xffffffffu, cand);
-    if (m == 0u) return;
-    if (cand) stage[staged + __popc(m & lt_mask)] = v;
-    staged += __popc(m);
-    if (staged > kCompStage - 32) flush();
+    if (ok & !(below | between)) {
+      queue[queued * 512] = v;
+      ++queued;
+    }
   };
   long long head = (4 - (long long)(((uintptr_t)x >> 2) & 3)) & 3;
   if (head > n) head = n;
@@ -446,22 +455,19 @@ select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectSta
     const long long e = threadIdx.x;
     const bool have = e < n_edge;
     const long long idx = e < head ? e : head + n4 * 4 + (e - head);
-    const float v = have ? x[idx] : 0.f;
-    append(classify(v, have), v);
+    take(have ? x[idx] : 0.f, have);
   }
-  const long long n4_pad = (n4 + 31) & ~31LL;
+  const long long n4_pad = (n4 + 31) & ~31LL;      // whole warps iterate together (the flush is warp-wide)
   for (long long i = tid; i < n4_pad; i += stride) {
     const bool ok = i < n4;
     const float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool k0 = classify(v.x, ok), k1 = classify(v.y, ok), k2 = classify(v.z, ok), k3 = classify(v.w, ok);
-    if (__any_sync(0xffffffffu, k0 | k1 | k2 | k3)) {
-      append(k0, v.x);
-      append(k1, v.y);
-      append(k2, v.z);
-      append(k3, v.w);
-    }
+    take(v.x, ok);
+    take(v.y, ok);
+    take(v.z, ok);
+    take(v.w, ok);
+    if (__any_sync(0xffffffffu, queued > kLaneQueue - 4)) flush();
   }
-  if (staged > 0) flush();
+  if (__any_sync(0xffffffffu, queued > 0)) flush();
   for (int o = 16; o > 0; o >>= 1) {
     c0 += __shfl_xor_sync(0xffffffffu, c0, o);
     c1 += __shfl_xor_sync(0xffffffffu, c1, o);
