@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(512)
 select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectState* __restrict__ s) {
   __shared__ unsigned long long lump[2];
   __shared__ float queue_all[512 * kLaneQueue];   // [slot][thread]: lane-private queues, conflict-free
+  __shared__ float gather_all[16][32 * kLaneQueue];   // per warp: the queues packed for a coalesced flush
   if (s->phase0 != 1 || s->status != MICA_NORM_PENDING || s->comp_cap <= 0) return;
   if (threadIdx.x < 2) lump[threadIdx.x] = 0ull;
   __syncthreads();
@@ -429,10 +430,13 @@ select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectSta
     unsigned long long base = 0;
     if (lane == 0) base = atomicAdd(&s->comp_count, (unsigned long long)total);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if ((long long)(base + total) <= comp_cap) {
-      const unsigned long long at = base + (unsigned long long)(incl - queued);
-      for (int q = 0; q < queued; ++q) comp[at + q] = queue[q * 512];
-    }
+    float* const pack = gather_all[threadIdx.x >> 5];
+    const int at = incl - queued;
+    for (int q = 0; q < queued; ++q) pack[at + q] = queue[q * 512];
+    __syncwarp();
+    if ((long long)(base + total) <= comp_cap)
+      for (int i = lane; i < total; i += 32) comp[base + i] = pack[i];
+    __syncwarp();
     queued = 0;
   };
   auto take = [&](float v, bool ok) {
