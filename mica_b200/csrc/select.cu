@@ -462,14 +462,27 @@ select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectSta
     take(have ? x[idx] : 0.f, have);
   }
   const long long n4_pad = (n4 + 31) & ~31LL;      // whole warps iterate together (the flush is warp-wide)
-  for (long long i = tid; i < n4_pad; i += stride) {
-    const bool ok = i < n4;
-    const float4 v = ok ? ld_stream4(x4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    take(v.x, ok);
-    take(v.y, ok);
-    take(v.z, ok);
-    take(v.w, ok);
-    if (__any_sync(0xffffffffu, queued > kLaneQueue - 4)) flush();
+  // four independent 16-byte loads in flight per thread: with one, 32 warps/SM keep only ~16 KB per SM on the
+  // way, half of what the HBM latency-bandwidth product asks for (ncu: 31 % of DRAM peak, long-scoreboard stalls)
+  constexpr int kDepth = 4;
+  for (long long i = tid; i < n4_pad; i += kDepth * stride) {
+    float4 v[kDepth];
+    bool ok[kDepth];
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+      const long long iu = i + u * stride;
+      ok[u] = iu < n4;
+      v[u] = ok[u] ? ld_stream4(x4 + iu) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kDepth; ++u) {
+      if (i + u * stride >= n4_pad) break;         // warp-uniform: i and stride are multiples of 32 apart per warp
+      take(v[u].x, ok[u]);
+      take(v[u].y, ok[u]);
+      take(v[u].z, ok[u]);
+      take(v[u].w, ok[u]);
+      if (__any_sync(0xffffffffu, queued > kLaneQueue - 4)) flush();
+    }
   }
   if (__any_sync(0xffffffffu, queued > 0)) flush();
   for (int o = 16; o > 0; o >>= 1) {
