@@ -909,8 +909,12 @@ def run_ours(args):
     dev_vols = vols                                                 # device volumes reused by every e2e step
 
     def time_e2e(out):
+        if world > 1:
+            dist.barrier()      # ranks leave the pinned allocation above seconds apart; the halo exchange waits, but not forever
         run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out, dev_vols)       # warm
         sync()
+        if world > 1:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             _, h2d_, d2h_ = run_map_pipeline_host(src_host, header, atoms_host, model_fn, pipe, out, dev_vols)

@@ -20,7 +20,7 @@ LIB = os.path.join(HERE, 'libmica_b200.so')
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
     '--ftz=false', '--prec-div=true', '--prec-sqrt=true',
-    '-Xcompiler', '-fPIC', '-Xcompiler', '-O2', '-shared',
+    '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '-shared',
 ]
 
 

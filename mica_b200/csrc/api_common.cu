@@ -1,5 +1,6 @@
 // Error plumbing and bookkeeping entry points of the C ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -19,6 +20,14 @@ int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return MICA_OK;
   int code = (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? MICA_ERR_NO_DEVICE : MICA_ERR_CUDA;
   return set_error(code, "%s: %s", what, cudaGetErrorString(e));
+}
+long long peer_timeout_cycles() {
+  long long ms = 60000;
+  if (const char* env = getenv("MICA_PEER_TIMEOUT_MS")) {
+    const long long v = atoll(env);
+    if (v > 0) ms = v;
+  }
+  return ms * 2000000LL;   // clock64 runs at <= 1.97 GHz on a B200
 }
 TensorMapEncodeFn tensor_map_encode_fn() {
   static TensorMapEncodeFn fn = nullptr;

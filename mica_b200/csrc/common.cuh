@@ -19,6 +19,12 @@ extern std::atomic<int64_t> g_launches;
 int set_error(int code, const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 
+// How long a kernel waits for a flag another rank raises over NVLink before it gives up with a status word
+// (clock64 ticks).  Ranks of one job can be SECONDS apart -- one still allocating 10 GB of pinned host memory,
+// another draining its volumes over a shared PCIe switch -- so the bound only has to beat "forever":
+// MICA_PEER_TIMEOUT_MS, default 60 s.
+long long peer_timeout_cycles();
+
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define MICA_CUDA(call)                                      \

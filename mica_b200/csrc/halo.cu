@@ -163,7 +163,7 @@ extern "C" int mica_halo_pull(float* dst_lo, int64_t n_lo, float* dst_hi, int64_
   MICA_REQUIRE((n_lo == 0 || dst_lo) && (n_hi == 0 || dst_hi), "null destination");
   if (world == 1) return MICA_OK;
   const int64_t padded = (slot_elems + 3) / 4 * 4;
-  const long long timeout_cycles = 4000000000LL;   // ~2 s at 1.9 GHz
+  const long long timeout_cycles = mica::peer_timeout_cycles();
   halo_pull_kernel<<<halo_grid(n_lo + n_hi), 256, 0, (cudaStream_t)stream>>>(
       dst_lo, n_lo, dst_hi, n_hi, peer_bufs, rank, world, parity, epoch, padded, timeout_cycles, status);
   MICA_LAUNCH_CHECK("halo_pull_kernel");

@@ -1128,7 +1128,7 @@ extern "C" int mica_select_peer_reduce(void* workspace, void* const* peer_bufs, 
   MICA_REQUIRE(workspace && peer_bufs, "null pointer");
   MICA_REQUIRE(world >= 1 && world <= kPeerMaxWorld && rank >= 0 && rank < world, "bad rank/world");
   MICA_REQUIRE(parity == 0 || parity == 1, "parity must be 0 or 1");
-  const long long timeout_cycles = 4000000000LL;   // ~2 s at 1.9 GHz
+  const long long timeout_cycles = mica::peer_timeout_cycles();
   select_peer_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
       state_of(workspace), reinterpret_cast<PeerBuffer* const*>(peer_bufs), rank, world, parity, epoch, step,
       timeout_cycles);

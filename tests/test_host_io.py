@@ -147,3 +147,41 @@ def test_next_row_mirrors_fail_loudly_without_a_gpu(tmp_path):
         lm.BackboneMask(p)
     with pytest.raises(_lib.MicaError):
         dm.DockingMapMasks()
+
+
+def test_native_pdb_parser_does_not_depend_on_the_number_of_pieces(tmp_path, monkeypatch):
+    """mica_parse_pdb cuts the text into pieces of whole lines, one host thread each; residue runs, MODEL
+    counts and duplicate-name detection that straddle a cut are stitched.  Every cut position must give the
+    result of the single-piece parse (and of the NumPy parser)."""
+    st = synthetic.synthetic_structure(40, (30, 30, 30), seed=5, hetero_every=7, unknown_every=5)
+    p = str(tmp_path / 's.pdb')
+    synthetic.write_pdb(p, st)
+    lines = open(p).read().splitlines()
+    atom_lines = [i for i, l in enumerate(lines) if l.startswith('ATOM')]
+    # an alternate location (same residue, same name) and two MODEL records in the middle of the file
+    dup = lines[atom_lines[20]]
+    dup = dup[:16] + 'B' + dup[17:54] + '  0.40' + dup[60:]
+    with_dup = lines[:atom_lines[20] + 1] + [dup] + lines[atom_lines[20] + 1:]
+    with_models = ['MODEL        1'] + lines[:atom_lines[60]] + ['ENDMDL', 'MODEL        2'] + lines[atom_lines[60]:]
+    for name, body in (('plain', lines), ('dup', with_dup), ('models', with_models)):
+        q = str(tmp_path / f'{name}.pdb')
+        with open(q, 'w') as fh:
+            fh.write('\n'.join(body) + '\n')
+        results = []
+        for threads, piece in ((1, 1 << 20), (2, 64), (5, 64), (16, 64), (64, 40)):
+            monkeypatch.setenv('MICA_PDB_THREADS', str(threads))
+            monkeypatch.setenv('MICA_PDB_MIN_PIECE', str(piece))
+            got = pdb._records_native(q, True)
+            extras = pdb._records_native.last
+            results.append(tuple(np.array(a) for a in got) + (extras['bb'].copy(), extras['aa'].copy(),
+                                                              extras['n_res'], extras['dup']))
+        for r in results[1:]:
+            for a, b in zip(results[0], r):
+                assert np.array_equal(a, b), name
+        assert results[0][-1] == (name == 'dup')
+        ref = pdb._records_numpy(q, True)
+        for a, b in zip(results[0][:4], ref):
+            assert np.array_equal(a, b), name
+        monkeypatch.delenv('MICA_PDB_THREADS')
+        monkeypatch.delenv('MICA_PDB_MIN_PIECE')
+        assert len(pdb.read_pdb_atoms(q)[0]) > 0
