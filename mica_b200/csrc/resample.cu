@@ -592,8 +592,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // ncu on the tile kernels above: the warps wait on shared memory inside the recursion and on the four
 // block-wide barriers per tile; 25-30 % of the HBM bandwidth.  This variant has NO shared memory and NO
 // barrier: a thread owns `len` consecutive samples of one column and computes everything it needs itself --
-// it reads its samples plus H before and H after straight from global memory (64-byte runs per row across
-// 16 lanes; the overlap with the neighbouring segments is served by L1), runs the causal recursion over
+// it reads its samples plus H before and H after straight from global memory (128-byte runs per row across
+// the warp; the overlap with the neighbouring segments is served by L1), runs the causal recursion over
 // all of them and the anticausal one back down, register to register.  Both recursions are one FMA per
 // sample: with d[k] = c[k] / (-z) the anticausal step c[k] = z (c[k+1] - c+[k]) becomes
 // d[k] = c+[k] + z d[k+1], the same form as the causal one; gain and -z are applied once per output.
@@ -605,10 +605,17 @@ constexpr int kColLen = 26;      // longest segment (registers: kColLen + kColH 
 // sample idx as float, `store(k, value)` takes the finished coefficient of sample k.  EDGE = the window leaves
 // [0, n): indices are mirrored (SciPy's boundary rule; running the recursions over the mirror image replaces the
 // closed-form end initialisation up to |pole|^H).
+// Only the kColLen samples a thread OWNS go through float64.  The H-sample run-in of the causal recursion,
+// the causal values of the H look-ahead samples and the run-in of the anticausal recursion are float32: an
+// error e in a run-in state reaches the first owned sample as |pole| e = 0.27 e and decays by 0.27 per sample,
+// i.e. <= 3e-8 relative, below the float32 rounding of what the pass stores.  That halves the dependent
+// float64 chain (100 -> 52 DFMA per segment; the float32 FMAs issue at twice the rate and half the latency)
+// and the f32 -> f64 conversions (58 -> 28).
 template <bool EDGE, typename Load, typename Store>
 __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k0, int k1) {
   constexpr int H = kColH, W = kColLen + 2 * kColH;
   const double z = kPole;
+  const float zf = (float)kPole;
   float x[W];
 #pragma unroll
   for (int i = 0; i < W; ++i) {
@@ -620,19 +627,28 @@ __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k
     }
     x[i] = load(idx);
   }
-  double cp[W - H];                               // causal values of samples k0 .. k0 + kColLen + H - 1
-  double st = 0.0;
+  float run = 0.f;                                // causal run-in over samples k0 - H .. k0 - 1
 #pragma unroll
-  for (int i = 0; i < H; ++i) st = fma(z, st, (double)x[i]);
+  for (int i = 0; i < H; ++i) run = fmaf(zf, run, x[i]);
+  double cp[kColLen];                             // causal values of the owned samples
+  double st = (double)run;
 #pragma unroll
-  for (int i = H; i < W; ++i) {
-    st = fma(z, st, (double)x[i]);
-    cp[i - H] = st;
+  for (int i = 0; i < kColLen; ++i) {
+    st = fma(z, st, (double)x[H + i]);
+    cp[i] = st;
+  }
+  float ahead[H];                                 // causal values of samples k0 + kColLen .. + H - 1
+  run = (float)st;
+#pragma unroll
+  for (int i = 0; i < H; ++i) {
+    run = fmaf(zf, run, x[H + kColLen + i]);
+    ahead[i] = run;
   }
   const double scale = -z * kGain;                // output = gain * c = gain * (-z) * d
-  double d = 0.0;
+  float back = 0.f;                               // anticausal run-in, downwards over the look-ahead samples
 #pragma unroll
-  for (int i = W - H - 1; i >= kColLen; --i) d = fma(z, d, cp[i]);
+  for (int i = H - 1; i >= 0; --i) back = fmaf(zf, back, ahead[i]);
+  double d = (double)back;
 #pragma unroll
   for (int i = kColLen - 1; i >= 0; --i) {     // store is called for every i, downwards (it may walk a pointer)
     d = fma(z, d, cp[i]);
@@ -660,15 +676,19 @@ __device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, fl
   }
 }
 
-template <int L, int THREADS>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
-cols_reg_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, ColStrides S, int len) {
-  const int j = threadIdx.x & (L - 1), seg = threadIdx.x / L;
-  const int col0 = blockIdx.x * L;
+// grid = (ceil(n_cols / 32), ceil(n_seg / 8), n_outer), block = 256: a WARP is 32 neighbouring columns of ONE
+// segment (128-byte runs per row; every lane takes the same interior / mirrored path -- with two segments per
+// warp a quarter of the warps ran both), the 8 warps of a CTA are 8 consecutive segments of those columns, so
+// the windows that overlap meet in the same L1.
+__global__ void __launch_bounds__(256, 2)
+cols_reg_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, ColStrides S, int len,
+                int n_seg) {
+  const int j = threadIdx.x & 31, seg = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int col = blockIdx.x * 32 + j;
   const int k0 = seg * len, k1 = min(n, k0 + len);
-  if (col0 + j >= n_cols || k0 >= k1) return;
-  const float* p = in + (int64_t)blockIdx.y * S.outer_in + col0 + j;
-  float* q = out + (int64_t)blockIdx.y * S.outer_out + col0 + j;
+  if (col >= n_cols || seg >= n_seg || k0 >= k1) return;
+  const float* p = in + (int64_t)blockIdx.z * S.outer_in + col;
+  float* q = out + (int64_t)blockIdx.z * S.outer_out + col;
   if (k0 - kColH >= 0 && k0 + kColLen + kColH <= n)
     cols_reg_segment<false>(p, q, S.line_in, S.line_out, n, k0, k1);
   else
@@ -1402,21 +1422,13 @@ static int launch_cols_pipe(const float* in, float* out, int n, int n_cols, int 
   if (cols_pipe_smem(n, 16) <= kPipeSmemMax) return launch_cols_pipe_t<16, 512>(in, out, n, n_cols, n_outer, S, st);
   return launch_cols_pipe_t<8, 512>(in, out, n, n_cols, n_outer, S, st);
 }
-// register-only column pass: 16 (or 8) columns x THREADS / L segments per CTA, segments of <= kColLen samples
+// register-only column pass: 32 columns x 8 segments per CTA, segments of <= kColLen samples
 static int launch_cols_reg(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
   if (n_cols <= 0 || n_outer <= 0) return MICA_OK;
   MICA_REQUIRE(n_outer <= 65535, "too many outer lines for the launch grid");
-  if (n <= 16 * kColLen) {
-    const int len = (n + 15) / 16;
-    cols_reg_kernel<16, 256><<<dim3((n_cols + 15) / 16, n_outer), 256, 0, st>>>(in, out, n, n_cols, S, len);
-  } else if (n <= 32 * kColLen) {
-    const int len = (n + 31) / 32;
-    cols_reg_kernel<16, 512><<<dim3((n_cols + 15) / 16, n_outer), 512, 0, st>>>(in, out, n, n_cols, S, len);
-  } else {
-    const int len = (n + 63) / 64;
-    MICA_REQUIRE(len <= kColLen, "line of %d samples too long for the register column pass", n);
-    cols_reg_kernel<8, 512><<<dim3((n_cols + 7) / 8, n_outer), 512, 0, st>>>(in, out, n, n_cols, S, len);
-  }
+  const int n_seg = (n + kColLen - 1) / kColLen;
+  const int len = (n + n_seg - 1) / n_seg;
+  cols_reg_kernel<<<dim3((n_cols + 31) / 32, (n_seg + 7) / 8, n_outer), 256, 0, st>>>(in, out, n, n_cols, S, len, n_seg);
   MICA_LAUNCH_CHECK("cols_reg_kernel");
   return MICA_OK;
 }

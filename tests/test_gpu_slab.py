@@ -179,9 +179,11 @@ def test_peer_memory_halo_exchange_assembles_the_source_planes(cuda, world):
     groups[0].close()
 
 
-def test_peer_halo_times_out_instead_of_hanging(cuda):
-    """A neighbour that never publishes turns into a status word after the bounded spin."""
+def test_peer_halo_times_out_instead_of_hanging(cuda, monkeypatch):
+    """A neighbour that never publishes turns into a status word after the bounded spin (MICA_PEER_TIMEOUT_MS;
+    60 s by default -- ranks of a real job can be seconds apart)."""
     from mica_b200.peer import PeerHalo
+    monkeypatch.setenv('MICA_PEER_TIMEOUT_MS', '1000')
     plan = SlabPlan((80, 8, 8), (np.float32(1.1),) * 3, 32, 16, 2)
     groups = PeerHalo.emulate(cuda, 2, 64 * 64)
     me = plan.ranks[0]
