@@ -443,10 +443,10 @@ select_guided_compact_kernel(const float* __restrict__ x, long long n, SelectSta
     const bool below = v < lo, between = (v >= hi) & (v < pt);
     c0 += (ok & below) ? 1u : 0u;
     c1 += (ok & between) ? 1u : 0u;
-    if (ok & !(below | between)) {
-      queue[queued * 512] = v;
-      ++queued;
-    }
+    // branch-free append: the value always lands in the lane's next free slot (the flush keeps at least
+    // four free), the slot is only kept when the voxel is a candidate
+    queue[queued * 512] = v;
+    queued += (ok & !(below | between)) ? 1 : 0;
   };
   long long head = (4 - (long long)(((uintptr_t)x >> 2) & 3)) & 3;
   if (head > n) head = n;
