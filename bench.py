@@ -452,6 +452,7 @@ def strong_720(ctx, identity):
         block['parity'] = {
             'against': 'the whole map on ONE GPU (run on every rank), pointwise stand-in model',
             'thresholds_bit_equal_all_ranks': thr_bad == 0.0, 'median': float(med_s), 'p999': float(p_s),
+            'median_one_gpu': float(single.median), 'p999_one_gpu': float(single.p999),
             'owned_slab_max_abs_all_ranks': worst_all, 'argmax_mismatch_frac_max': mism_all,
             'rank0': dict(diffs, normalized=norm_diff),
             'ok': bool(thr_bad == 0.0 and worst_all <= 1e-6 and mism_all <= 1e-6),

@@ -605,15 +605,19 @@ constexpr int kColLen = 26;      // longest segment (registers: kColLen + kColH 
 // sample idx as float, `store(k, value)` takes the finished coefficient of sample k.  EDGE = the window leaves
 // [0, n): indices are mirrored (SciPy's boundary rule; running the recursions over the mirror image replaces the
 // closed-form end initialisation up to |pole|^H).
-// Only the kColLen samples a thread OWNS go through float64.  The H-sample run-in of the causal recursion,
-// the causal values of the H look-ahead samples and the run-in of the anticausal recursion are float32: an
-// error e in a run-in state reaches the first owned sample as |pole| e = 0.27 e and decays by 0.27 per sample,
-// i.e. <= 3e-8 relative, below the float32 rounding of what the pass stores.  That halves the dependent
-// float64 chain (100 -> 52 DFMA per segment; the float32 FMAs issue at twice the rate and half the latency)
-// and the f32 -> f64 conversions (58 -> 28).
+// Only the kColLen samples a thread OWNS and kNear samples either side of them go through float64.  The far
+// part of the H-sample run-in of the causal recursion, the causal values of the far look-ahead samples and the far
+// part of the run-in of the anticausal recursion are float32: an error e in such a state reaches the first owned
+// sample as |pole|^(kNear+1) e = 1.4e-3 e and decays by 0.27 per sample, i.e. <= 2e-10 relative -- below the
+// 7e-10 the finite horizon costs anyway, so a line cut into different segments (a z-slab of a map against the
+// whole map) still rounds to the same float32 coefficients.  That shortens the dependent float64 chain from
+// 100 to 68 DFMA per segment (the float32 FMAs issue at twice the rate and half the latency) and saves 24 of
+// the 58 f32 -> f64 conversions.
+constexpr int kNear = 4;
+
 template <bool EDGE, typename Load, typename Store>
 __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k0, int k1) {
-  constexpr int H = kColH, W = kColLen + 2 * kColH;
+  constexpr int H = kColH, W = kColLen + 2 * kColH, F = kColH - kNear;   // F far samples on either side
   const double z = kPole;
   const float zf = (float)kPole;
   float x[W];
@@ -627,28 +631,32 @@ __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k
     }
     x[i] = load(idx);
   }
-  float run = 0.f;                                // causal run-in over samples k0 - H .. k0 - 1
+  float run = 0.f;                                // causal run-in, far part: samples k0 - H .. k0 - kNear - 1
 #pragma unroll
-  for (int i = 0; i < H; ++i) run = fmaf(zf, run, x[i]);
-  double cp[kColLen];                             // causal values of the owned samples
+  for (int i = 0; i < F; ++i) run = fmaf(zf, run, x[i]);
   double st = (double)run;
 #pragma unroll
-  for (int i = 0; i < kColLen; ++i) {
+  for (int i = F; i < H; ++i) st = fma(z, st, (double)x[i]);
+  double cp[kColLen + kNear];                     // causal values of the owned samples and the kNear after them
+#pragma unroll
+  for (int i = 0; i < kColLen + kNear; ++i) {
     st = fma(z, st, (double)x[H + i]);
     cp[i] = st;
   }
-  float ahead[H];                                 // causal values of samples k0 + kColLen .. + H - 1
+  float ahead[F];                                 // causal values of the far look-ahead samples
   run = (float)st;
 #pragma unroll
-  for (int i = 0; i < H; ++i) {
-    run = fmaf(zf, run, x[H + kColLen + i]);
+  for (int i = 0; i < F; ++i) {
+    run = fmaf(zf, run, x[H + kColLen + kNear + i]);
     ahead[i] = run;
   }
   const double scale = -z * kGain;                // output = gain * c = gain * (-z) * d
-  float back = 0.f;                               // anticausal run-in, downwards over the look-ahead samples
+  float back = 0.f;                               // anticausal run-in, downwards: far part, then the near samples
 #pragma unroll
-  for (int i = H - 1; i >= 0; --i) back = fmaf(zf, back, ahead[i]);
+  for (int i = F - 1; i >= 0; --i) back = fmaf(zf, back, ahead[i]);
   double d = (double)back;
+#pragma unroll
+  for (int i = kColLen + kNear - 1; i >= kColLen; --i) d = fma(z, d, cp[i]);
 #pragma unroll
   for (int i = kColLen - 1; i >= 0; --i) {     // store is called for every i, downwards (it may walk a pointer)
     d = fma(z, d, cp[i]);
