@@ -11,8 +11,6 @@
 // reference too), so each output voxel is written exactly once: no atomics, no weights.
 // One thread per core voxel, the cube's fastest axis across the warp: 26 coalesced
 // channel reads (stride W^3) and 23 coalesced writes per voxel.
-#include <stdlib.h>
-
 #include "common.cuh"
 
 namespace mica {
@@ -129,105 +127,6 @@ postproc_stitch_kernel(StitchParams P, StitchOwners O) {
     for (int t = 0; t < 20; ++t) st_stream(P.aa_prob_vol + (int64_t)t * vol_n + dst, l[t] * r);
     st_stream(P.aa_pred_vol + dst, (float)arg);
   }
-}
-
-// Two voxels per thread, two cubes per warp.  What a B200 takes for writes depends on the size of the contiguous
-// pieces an instruction stream produces (tools/micro/writebw.cu: 4.0 TB/s for 128-byte pieces, 6.7 TB/s for 256
-// bytes, 7.5 TB/s from 512 bytes): a core row of a stride-32 cube is one 128-byte piece of an output row, the next
-// piece belongs to the next cube of the batch.  Here a thread owns voxels c, c + 1 of a row (8-byte loads and
-// stores), a half-warp owns a row of ONE cube and the two halves of a warp the same row of two cubes that follow
-// each other in the batch -- neighbours along the volume's fastest axis whenever the batch is in raster order, so
-// a store instruction writes 256 contiguous bytes.  Needs even Z extents / origins / padding (8-byte alignment);
-// everything else takes the kernel above.  grid = (ceil(B / 2), S * ceil(S * S / 2 / 128)), block = 256.
-__device__ __forceinline__ float2 ld_stream_half_line2(const float* p) {
-  float2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-__device__ __forceinline__ void st_stream2(float* p, float a, float b) {
-  asm volatile("st.global.cs.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(a), "f"(b) : "memory");
-}
-
-template <bool PEER>
-__global__ void __launch_bounds__(256)
-postproc_stitch2_kernel(StitchParams P, StitchOwners O, int n_cubes) {
-  const int S = P.S, W = P.W, half_row = S >> 1;
-  const int per_plane = S * half_row;                       // float2 elements of one core plane
-  const int chunks = (per_plane + 127) >> 7;
-  const int a = blockIdx.y / chunks;
-  const int b = 2 * blockIdx.x + ((threadIdx.x >> 4) & 1);
-  if (b >= n_cubes) return;
-  const int i = P.ijk[3 * b + 0], j = P.ijk[3 * b + 1], k = P.ijk[3 * b + 2];
-  const int gx = i + a;
-  if (gx >= P.X || gx < P.org[0] || gx >= P.org[0] + P.ext[0]) return;
-  const int64_t W3 = (int64_t)W * W * W;
-  const float* bb = P.bb + (int64_t)b * 4 * W3;
-  const float* ca = P.ca + (int64_t)b * 4 * W3;
-  const float* aa = P.aa + (int64_t)b * 21 * W3;
-  int64_t vol_n = (int64_t)P.ext[0] * P.ext[1] * P.ext[2];
-  int x_org = P.org[0];
-  if (PEER) {
-    int r = 0;
-    while (r + 1 < O.world && gx >= O.bounds[r + 1]) ++r;
-    x_org = O.bounds[r];
-    vol_n = (int64_t)(O.bounds[r + 1] - O.bounds[r]) * P.ext[1] * P.ext[2];
-    float* base = O.base[r];
-    P.bb_vol = base;
-    P.ca_vol = base + vol_n;
-    P.aa_pred_vol = base + 2 * vol_n;
-    P.aa_prob_vol = base + 3 * vol_n;
-  }
-  const int e = (blockIdx.y - a * chunks) * 128 + ((threadIdx.x >> 5) << 4) + (threadIdx.x & 15);
-  if (e >= per_plane) return;
-  const int bj = e / half_row, c = (e - bj * half_row) << 1;
-  const int gy = j + bj, gz = k + c;
-  if (gy >= P.Y || gz >= P.Z) return;                       // Z is even: gz + 1 < Z as well
-  const int ly = gy - P.org[1], lz = gz - P.org[2];
-  if ((unsigned)ly >= (unsigned)P.ext[1] || (unsigned)lz >= (unsigned)P.ext[2]) return;
-  const int64_t src = ((int64_t)(a + P.pad) * W + (bj + P.pad)) * W + (c + P.pad);
-  const int64_t dst = ((int64_t)(gx - x_org) * P.ext[1] + ly) * P.ext[2] + lz;
-  const float2 b0 = ld_stream_half_line2(bb + src), b2 = ld_stream_half_line2(bb + 2 * W3 + src),
-               b3 = ld_stream_half_line2(bb + 3 * W3 + src);
-  const float2 c0 = ld_stream_half_line2(ca + src), c2 = ld_stream_half_line2(ca + 2 * W3 + src),
-               c3 = ld_stream_half_line2(ca + 3 * W3 + src);
-  float2 l[20];
-#pragma unroll
-  for (int t = 0; t < 20; ++t) l[t] = ld_stream_half_line2(aa + (int64_t)(t + 1) * W3 + src);
-  st_stream2(P.bb_vol + dst, softmax3_last(b0.x, b2.x, b3.x), softmax3_last(b0.y, b2.y, b3.y));
-  st_stream2(P.ca_vol + dst, softmax3_last(c0.x, c2.x, c3.x), softmax3_last(c0.y, c2.y, c3.y));
-  float mx = l[0].x, my = l[0].y;
-  int ax = 0, ay = 0;
-#pragma unroll
-  for (int t = 1; t < 20; ++t) {
-    if (l[t].x > mx) {
-      mx = l[t].x;
-      ax = t;
-    }
-    if (l[t].y > my) {
-      my = l[t].y;
-      ay = t;
-    }
-  }
-  float sx = 0.f, sy = 0.f;
-#pragma unroll
-  for (int t = 0; t < 20; ++t) {
-    l[t].x = exp_neg(l[t].x - mx);
-    l[t].y = exp_neg(l[t].y - my);
-    sx += l[t].x;
-    sy += l[t].y;
-  }
-  const float rx = __frcp_rn(sx), ry = __frcp_rn(sy);
-#pragma unroll
-  for (int t = 0; t < 20; ++t) st_stream2(P.aa_prob_vol + (int64_t)t * vol_n + dst, l[t].x * rx, l[t].y * ry);
-  st_stream2(P.aa_pred_vol + dst, (float)ax, (float)ay);
-}
-
-// the pair kernel needs every 8-byte access aligned: even window geometry, even Z extent and origin, aligned bases
-static bool pair_kernel_ok(const StitchParams& P, int64_t vol_n_parity) {
-  if (getenv("MICA_STITCH_SCALAR")) return false;
-  if ((P.S & 1) || (P.pad & 1) || (P.W & 1) || (P.Z & 1) || (P.ext[2] & 1) || (P.org[2] & 1) || (vol_n_parity & 1)) return false;
-  const uintptr_t all = (uintptr_t)P.bb | (uintptr_t)P.ca | (uintptr_t)P.aa;
-  return (all & 7) == 0;
 }
 
 // ---------------------------------------------------------------- overlap-weighted stitching (north_star variant)
@@ -408,15 +307,8 @@ extern "C" int mica_postproc_stitch(const float* bb, const float* ca, const floa
     P.ca = ca + (int64_t)b0 * 4 * W3;
     P.aa = aa + (int64_t)b0 * 21 * W3;
     P.ijk = ijk + 3 * (int64_t)b0;
-    const uintptr_t vols = (uintptr_t)bb_vol | (uintptr_t)ca_vol | (uintptr_t)aa_prob_vol | (uintptr_t)aa_pred_vol;
-    if (pair_kernel_ok(P, (int64_t)ext[0] * ext[1] * ext[2]) && (vols & 7) == 0 && (b0 & 1) == 0) {
-      const int chunks2 = (grid_size * (grid_size / 2) + 127) / 128;
-      postproc_stitch2_kernel<false><<<dim3((nb + 1) / 2, grid_size * chunks2), 256, 0, (cudaStream_t)stream>>>(
-          P, StitchOwners(), nb);
-    } else {
-      const int chunks = (grid_size * grid_size + 255) / 256;
-      postproc_stitch_kernel<false><<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P, StitchOwners());
-    }
+    const int chunks = (grid_size * grid_size + 255) / 256;
+    postproc_stitch_kernel<false><<<dim3(nb, grid_size * chunks), 256, 0, (cudaStream_t)stream>>>(P, StitchOwners());
     MICA_LAUNCH_CHECK("postproc_stitch_kernel");
   }
   return MICA_OK;

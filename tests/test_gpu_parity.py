@@ -520,7 +520,8 @@ def _check_stitched(want, got, logits):
     assert diff.mean() < 1e-4
 
 
-@pytest.mark.parametrize('cube_shape,gs,pad', [((52, 20, 12), 48, 8), ((70, 33, 50), 32, 16), ((21, 13, 9), 8, 2)])
+@pytest.mark.parametrize('cube_shape,gs,pad', [((52, 20, 12), 48, 8), ((70, 33, 50), 32, 16), ((21, 13, 9), 8, 2),
+                                               ((20, 24, 90), 32, 16), ((40, 31, 49), 32, 16)])
 def test_postproc_stitch_vs_oracle(cuda, cube_shape, gs, pad):
     want, got, logits = _stitch_case(cube_shape, gs, pad, cuda)
     _check_stitched(want, got, logits)

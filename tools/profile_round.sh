@@ -9,7 +9,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
     --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 2 --warmup 1 $SHORT \
     > gpurun_out/ncu_launches_${TAG}.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'postproc_stitch|march_yz|cols_reg|rows_pipe|select_guided|select_hist|normalize_apply|extract_tma|af3_fill|af3_bin' -c 26 \
+    -k regex:'postproc_stitch|march_yz|cols_reg|rows_pipe|rows_reg|select_guided|select_hist|normalize_apply|extract_tma|af3_fill|af3_bin' -c 26 \
     -o gpurun_out/prof_${TAG} python bench.py --steps 1 --warmup 0 $SHORT \
     > gpurun_out/ncu_full_${TAG}.log 2>&1
 ls -la gpurun_out | tail -8
