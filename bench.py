@@ -455,9 +455,11 @@ def strong_720(ctx, identity):
             'median_one_gpu': float(single.median), 'p999_one_gpu': float(single.p999),
             'owned_slab_max_abs_all_ranks': worst_all, 'argmax_mismatch_frac_max': mism_all,
             'rank0': dict(diffs, normalized=norm_diff),
+            'bit_identical_all_ranks': bool(thr_bad == 0.0 and worst_all == 0.0 and mism_all == 0.0),
             'ok': bool(thr_bad == 0.0 and worst_all <= 1e-6 and mism_all <= 1e-6),
             'tolerance': 'thresholds bit-equal; normalised planes and probability volumes <= 1e-6; argmax '
-                         'mismatches <= 1e-6 of the voxels (ties after a 1e-7 input difference)',
+                         'mismatches <= 1e-6 of the voxels.  A rank holds whole prefilter windows of its planes '
+                         '(SlabPlan aligned=True), so the expected difference is exactly 0 (bit_identical_all_ranks)',
         }
         del v_slab, v_full, single
     del pipe, src_full, own

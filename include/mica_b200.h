@@ -72,11 +72,19 @@ size_t mica_resample_workspace_bytes(int src_nz_local, int sy, int sx, int nz, i
  * Returns the previous setting.  Both routes implement the same arithmetic. */
 int mica_resample_force_generic(int on);
 
+/* host: the block of source planes [*src_lo, *src_hi) a rank should hold to resample output planes
+ * [dst_z0, dst_z0+dst_nz_local) of a map with sz source / nz output planes (no reference counterpart:
+ * the z-slab partition of SURVEY 8e).  The z prefilter cuts a line into the same segments whichever
+ * block of it is in memory; with this block every coefficient the slab needs is computed from the same
+ * window as on the whole map, so the slab's planes are BIT-IDENTICAL to the whole map's. */
+int mica_resample_slab_source_planes(int sz, int nz, int dst_z0, int dst_nz_local, int* src_lo, int* src_hi);
+
 /* src: device float32 [src_nz_local, sy, sx] = global source planes [src_z0, src_z0+src_nz_local)
  * dst: device float32 [dst_nz_local, ny, nx] = global output planes [dst_z0, dst_z0+dst_nz_local)
- * (sz,sy,sx) / (nz,ny,nx) are the GLOBAL source / output shapes.  With a partial
- * slab the z prefilter is run on the slab alone (mirror at its ends); the caller
- * supplies >= 16 halo planes beyond the taps it needs (error < 1e-9).
+ * (sz,sy,sx) / (nz,ny,nx) are the GLOBAL source / output shapes.  With a partial slab the z prefilter
+ * runs on the block alone: bit-identical to the whole map when the block is the one
+ * mica_resample_slab_source_planes names; with any block that holds >= 16 planes beyond the taps the
+ * output needs, a window that leaves the block is reflected at its end (error < 1e-9).
  */
 int mica_bspline_resample_f32(const float* src, int sz, int sy, int sx, int src_z0, int src_nz_local,
                               float* dst, int nz, int ny, int nx, int dst_z0, int dst_nz_local,

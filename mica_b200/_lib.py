@@ -42,6 +42,7 @@ SIGNATURES = {
     'mica_zoom_output_shape': (_i, [C.POINTER(_i), C.POINTER(_f), C.POINTER(_i)]),
     'mica_resample_workspace_bytes': (_sz, [_i] * 7),
     'mica_resample_force_generic': (_i, [_i]),
+    'mica_resample_slab_source_planes': (_i, [_i, _i, _i, _i, _p, _p]),
     'mica_bspline_resample_f32': (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     'mica_select_workspace_bytes': (_sz, []),
     'mica_select_workspace_bytes_for': (_sz, [_i64]),

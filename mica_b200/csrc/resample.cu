@@ -664,43 +664,60 @@ __device__ __forceinline__ void reg_segment(Load load, Store store, int n, int k
   }
 }
 
+// `n` samples of the line are in memory, samples [g0, g0 + n) of a line of `ng` (a z-slab of a map holds a block
+// of every z line; g0 = 0, ng = n otherwise).  k0, k1 and the window are GLOBAL sample numbers: the segments of a
+// block are the segments the whole line would be cut into, so a coefficient is computed from the same window by
+// the same operations whichever rank holds it -- bit-identical, as long as the block contains the window
+// (SlabPlan sizes the halo for that).  A window that leaves the block without leaving the line (a halo shorter
+// than that) is reflected at the block end: >= kColH real samples away from every coefficient the caller
+// needs, the accuracy of the finite horizon, no longer the identical bits.
 template <bool EDGE>
 __device__ __forceinline__ void cols_reg_segment(const float* __restrict__ p, float* __restrict__ q, int64_t line_in,
-                                                 int64_t line_out, int n, int k0, int k1) {
-  float* o = q + (int64_t)(k0 + kColLen - 1) * line_out;
-  auto store = [&](int, double v, bool on) {
-    if (on) *o = (float)v;
-    o -= line_out;
-  };
+                                                 int64_t line_out, int n, int g0, int ng, int k0, int k1) {
+  float* o = q + (int64_t)(k0 - g0 + kColLen - 1) * line_out;
   if (EDGE) {
-    reg_segment<true>([&](int idx) { return __ldg(p + (int64_t)idx * line_in); }, store, n, k0, k1);
+    auto store = [&](int k, double v, bool on) {
+      if (on && k >= g0 && k < g0 + n) *o = (float)v;
+      o -= line_out;
+    };
+    reg_segment<true>([&](int idx) {
+      int l = idx - g0;
+      l = l < 0 ? -l : l;
+      l = l > n - 1 ? 2 * (n - 1) - l : l;
+      l = l < 0 ? 0 : l;
+      return __ldg(p + (int64_t)l * line_in);
+    }, store, ng, k0, k1);
   } else {   // interior windows are read in increasing order: walk the column with pointer increments only
-    const float* r = p + (int64_t)(k0 - kColH) * line_in;
+    auto store = [&](int, double v, bool on) {
+      if (on) *o = (float)v;
+      o -= line_out;
+    };
+    const float* r = p + (int64_t)(k0 - g0 - kColH) * line_in;
     reg_segment<false>([&](int) {
       const float v = __ldg(r);
       r += line_in;
       return v;
-    }, store, n, k0, k1);
+    }, store, ng, k0, k1);
   }
 }
 
 // grid = (ceil(n_cols / 32), ceil(n_seg / 8), n_outer), block = 256: a WARP is 32 neighbouring columns of ONE
 // segment (128-byte runs per row; every lane takes the same interior / mirrored path -- with two segments per
 // warp a quarter of the warps ran both), the 8 warps of a CTA are 8 consecutive segments of those columns, so
-// the windows that overlap meet in the same L1.
+// the windows that overlap meet in the same L1.  Segments seg0 .. seg0 + n_seg - 1 of the global line are run.
 __global__ void __launch_bounds__(256, 2)
 cols_reg_kernel(const float* __restrict__ in, float* __restrict__ out, int n, int n_cols, ColStrides S, int len,
-                int n_seg) {
+                int n_seg, int g0, int ng, int seg0) {
   const int j = threadIdx.x & 31, seg = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int col = blockIdx.x * 32 + j;
-  const int k0 = seg * len, k1 = min(n, k0 + len);
+  const int k0 = (seg0 + seg) * len, k1 = min(ng, k0 + len);
   if (col >= n_cols || seg >= n_seg || k0 >= k1) return;
   const float* p = in + (int64_t)blockIdx.z * S.outer_in + col;
   float* q = out + (int64_t)blockIdx.z * S.outer_out + col;
-  if (k0 - kColH >= 0 && k0 + kColLen + kColH <= n)
-    cols_reg_segment<false>(p, q, S.line_in, S.line_out, n, k0, k1);
+  if (k0 - kColH >= g0 && k0 + kColLen + kColH <= g0 + n)
+    cols_reg_segment<false>(p, q, S.line_in, S.line_out, n, g0, ng, k0, k1);
   else
-    cols_reg_segment<true>(p, q, S.line_in, S.line_out, n, k0, k1);
+    cols_reg_segment<true>(p, q, S.line_in, S.line_out, n, g0, ng, k0, k1);
 }
 
 // ------------------------------------------------- cp.async-pipelined prefilter passes (fast path)
@@ -1398,10 +1415,46 @@ static size_t rows_pipe_smem(int n, int L) {
   return (((size_t)L * (n | 1) * 8 + 15) & ~(size_t)15) + (size_t)kPipeStages * L * pitch_f32(n) * 4;
 }
 
-static bool fast_path_ok(int src_nz_local, int sy, int sx, int ny, int nx) {
+// Source planes [*c_lo, *c_hi] (global) that hold a z tap of output planes [dst_z0, dst_z0 + dst_nz_local), with
+// one plane of margin on either side, clipped to the block [src_z0, src_z0 + src_nz_local).
+static void needed_planes(int sz, int nz, int dst_z0, int dst_nz_local, int src_z0, int src_nz_local, int* c_lo,
+                          int* c_hi) {
+  const double zoom = nz > 1 ? (double)(sz - 1) / (double)(nz - 1) : 1.0;
+  int lo = (int)floor((double)dst_z0 * zoom) - 2, hi = (int)floor((double)(dst_z0 + dst_nz_local - 1) * zoom) + 3;
+  lo = lo < src_z0 ? src_z0 : lo;
+  hi = hi > src_z0 + src_nz_local - 1 ? src_z0 + src_nz_local - 1 : hi;
+  if (dst_z0 + dst_nz_local >= nz) hi = src_z0 + src_nz_local - 1;   // the parked window of an all-zero last plane (D11)
+  if (hi < lo) lo = src_z0, hi = src_z0 + src_nz_local - 1;
+  *c_lo = lo;
+  *c_hi = hi;
+}
+
+// Block of source planes [*src_lo, *src_hi) a rank must hold so that the z prefilter of output planes
+// [dst_z0, dst_z0 + dst_nz_local) sees the windows the whole map would give it (bit-identical coefficients).
+extern "C" int mica_resample_slab_source_planes(int sz, int nz, int dst_z0, int dst_nz_local, int* src_lo, int* src_hi) {
+  MICA_REQUIRE(src_lo && src_hi, "null pointer");
+  MICA_REQUIRE(sz > 0 && nz > 0 && dst_z0 >= 0 && dst_nz_local > 0 && dst_z0 + dst_nz_local <= nz, "bad slab");
+  int c_lo, c_hi, n_seg, len;
+  needed_planes(sz, nz, dst_z0, dst_nz_local, 0, sz, &c_lo, &c_hi);
+  n_seg = (sz + kColLen - 1) / kColLen;
+  len = (sz + n_seg - 1) / n_seg;
+  const int lo = c_lo / len * len - kColH, hi = c_hi / len * len + kColLen + kColH;
+  *src_lo = lo < 0 ? 0 : lo;
+  *src_hi = hi > sz ? sz : hi;
+  return MICA_OK;
+}
+
+static bool reg_cols_ok(int src_nz_local, int sy) {
+  return !getenv("MICA_RESAMPLE_NOREG") && src_nz_local <= 64 * kColLen && sy <= 64 * kColLen;
+}
+// sz = planes of the whole map, src_nz_local = planes of the block in memory.  The choice follows the WHOLE line
+// wherever it can, so that a thin block of a long line (the last rank of a z-slab partition) runs the same
+// arithmetic as the whole map: the register column pass takes a block of any length.
+static bool fast_path_ok(int sz, int src_nz_local, int sy, int sx, int ny, int nx) {
   if (g_force_generic || getenv("MICA_NO_TMA") || getenv("MICA_RESAMPLE_OLD")) return false;
   if (src_nz_local > 1760 || sy > 1760 || sx > 1760) return false;   // 64 segments x kRegSeg samples, tile in smem
-  if (src_nz_local < kMinSegLine || sy < kMinSegLine || sx < kMinSegLine) return false;   // segment-parallel sweeps
+  if (sz < kMinSegLine || sy < kMinSegLine || sx < kMinSegLine) return false;             // segment-parallel sweeps
+  if (src_nz_local < (reg_cols_ok(src_nz_local, sy) ? 8 : kMinSegLine)) return false;
   if (cols_pipe_smem(src_nz_local, 8) > kPipeSmemMax || cols_pipe_smem(sy, 8) > kPipeSmemMax ||
       rows_pipe_smem(sx, 8) > kPipeSmemMax)
     return false;
@@ -1430,15 +1483,27 @@ static int launch_cols_pipe(const float* in, float* out, int n, int n_cols, int 
   if (cols_pipe_smem(n, 16) <= kPipeSmemMax) return launch_cols_pipe_t<16, 512>(in, out, n, n_cols, n_outer, S, st);
   return launch_cols_pipe_t<8, 512>(in, out, n, n_cols, n_outer, S, st);
 }
-// register-only column pass: 32 columns x 8 segments per CTA, segments of <= kColLen samples
-static int launch_cols_reg(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
-  if (n_cols <= 0 || n_outer <= 0) return MICA_OK;
+// register-only column pass: 32 columns x 8 segments per CTA, segments of <= kColLen samples.  The line in memory
+// is samples [g0, g0 + n) of a line of ng; the segments of the GLOBAL line that hold samples [need_lo, need_hi]
+// (global numbers) are computed.
+static void cols_reg_geometry(int ng, int* n_seg, int* len) {
+  *n_seg = (ng + kColLen - 1) / kColLen;
+  *len = (ng + *n_seg - 1) / *n_seg;
+}
+static int launch_cols_reg(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st,
+                           int g0, int ng, int need_lo, int need_hi) {
+  if (n_cols <= 0 || n_outer <= 0 || need_hi < need_lo) return MICA_OK;
   MICA_REQUIRE(n_outer <= 65535, "too many outer lines for the launch grid");
-  const int n_seg = (n + kColLen - 1) / kColLen;
-  const int len = (n + n_seg - 1) / n_seg;
-  cols_reg_kernel<<<dim3((n_cols + 31) / 32, (n_seg + 7) / 8, n_outer), 256, 0, st>>>(in, out, n, n_cols, S, len, n_seg);
+  int n_seg_g, len;
+  cols_reg_geometry(ng, &n_seg_g, &len);
+  const int seg0 = need_lo / len, n_seg = need_hi / len - seg0 + 1;
+  cols_reg_kernel<<<dim3((n_cols + 31) / 32, (n_seg + 7) / 8, n_outer), 256, 0, st>>>(in, out, n, n_cols, S, len, n_seg,
+                                                                                   g0, ng, seg0);
   MICA_LAUNCH_CHECK("cols_reg_kernel");
   return MICA_OK;
+}
+static int launch_cols_reg(const float* in, float* out, int n, int n_cols, int n_outer, ColStrides S, cudaStream_t st) {
+  return launch_cols_reg(in, out, n, n_cols, n_outer, S, st, 0, n, 0, n - 1);
 }
 
 template <int L, int THREADS>
@@ -1525,7 +1590,7 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
   MICA_LAUNCH_CHECK("taps_kernel(x)");
 
   dim3 grid((nx + 127) / 128, ny, dst_nz_local);
-  if (order == 3 && fast_path_ok(src_nz_local, sy, sx, ny, nx)) {
+  if (order == 3 && fast_path_ok(sz, src_nz_local, sy, sx, ny, nx)) {
     const int64_t plane = (int64_t)sy * sx;
     MICA_REQUIRE(plane <= 0x7fffffffLL && src_nz_local <= 65535 && sy <= 65535, "source plane too large");
     const int64_t p32 = pitch_f32(sx), p64 = pitch_f64(nx);
@@ -1533,14 +1598,20 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
     double* xr = (double*)((char*)coeff + align_up((size_t)2 * src_nz_local * sy * p32 * sizeof(float), 256));
     // axis 0 (z): columns (y, x0..x0+15) of length src_nz_local; float32 in (row pitch sx), float32 out (pitch p32)
     const bool pipe = !getenv("MICA_RESAMPLE_NOPIPE");
-    const bool regcols = !getenv("MICA_RESAMPLE_NOREG") && src_nz_local <= 64 * kColLen && sy <= 64 * kColLen;
+    const bool regcols = reg_cols_ok(src_nz_local, sy);
     float* c32b = c32 + (size_t)src_nz_local * sy * p32;      // second float32 volume (the register pass is not in place)
     const ColStrides Sz{plane, sy * p32, sx, p32}, Sy{p32, p32, sy * p32, sy * p32};
     int rc;
+    // source planes whose coefficients the z taps of this output slab can touch (global numbers, one plane of
+    // margin): the whole line for a whole map; for a z-slab the planes beyond them are prefilter horizon only
+    // and take no part in the y and x passes
+    int c_lo, c_hi;
+    needed_planes(sz, nz, dst_z0, dst_nz_local, src_z0, src_nz_local, &c_lo, &c_hi);
+    const int l0 = c_lo - src_z0, cnt = c_hi - c_lo + 1;
     if (regcols) {
-      rc = launch_cols_reg(src, c32b, src_nz_local, sx, sy, Sz, st);
+      rc = launch_cols_reg(src, c32b, src_nz_local, sx, sy, Sz, st, src_z0, sz, c_lo, c_hi);
       if (rc) return rc;
-      rc = launch_cols_reg(c32b, c32, sy, sx, src_nz_local, Sy, st);
+      rc = launch_cols_reg(c32b + (size_t)l0 * sy * p32, c32 + (size_t)l0 * sy * p32, sy, sx, cnt, Sy, st);
     } else {
       rc = pipe ? launch_cols_pipe(src, c32, src_nz_local, sx, sy, Sz, st)
                 : launch_cols<float, float>(src, c32, src_nz_local, sx, sy, Sz, st);
@@ -1552,7 +1623,8 @@ extern "C" int mica_bspline_resample_f32(const float* src, int sz, int sy, int s
     if (rc) return rc;
     // axis 2 (x): prefilter + interpolate the rows -> x-resampled float64 volume
     if (pipe) {
-      rc = launch_rows_pipe(c32, p32, xr, p64, sx, nx, (int64_t)src_nz_local * sy, tx, st);
+      rc = launch_rows_pipe(c32 + (size_t)l0 * sy * p32, p32, xr + (size_t)l0 * sy * p64, p64, sx, nx, (int64_t)cnt * sy,
+                            tx, st);
       if (rc) return rc;
     } else {
       const int64_t n_rows = (int64_t)src_nz_local * sy;

@@ -85,6 +85,15 @@ def zoom_output_shape(in_zyx, zoom_zyx):
     return tuple(int(v) for v in out)
 
 
+def resample_slab_source_planes(sz: int, nz: int, dst_z0: int, dst_nz_local: int):
+    """Source planes [lo, hi) a rank holds so that its output planes [dst_z0, dst_z0+dst_nz_local) come out
+    bit-identical to the whole map's (the z prefilter's segments and windows are those of the whole line)."""
+    lo, hi = C.c_int(), C.c_int()
+    check(lib.mica_resample_slab_source_planes(int(sz), int(nz), int(dst_z0), int(dst_nz_local),
+                                               C.byref(lo), C.byref(hi)), 'resample_slab_source_planes')
+    return int(lo.value), int(hi.value)
+
+
 @device_guard
 def resample(src: torch.Tensor, out_shape, order: int = 3, *, src_z0: int = 0, src_shape=None,
              dst_z0: int = 0, dst_nz_local=None, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -6,8 +6,10 @@ every stitched voxel -- has exactly one owner.  Per stage:
 
   resample      each rank resamples its owned output planes plus ``padding`` halo planes
                 (the cube windows reach that far) from its source planes plus the
-                interpolation taps plus ``halo_k`` planes of prefilter horizon; the source
-                halo comes from the neighbouring ranks by send/recv (NCCL over NVLink).
+                interpolation taps plus the prefilter windows of the segments that hold them
+                (>= ``halo_k`` planes of horizon; whole segments, so that the result is
+                bit-identical to the one-GPU map); the source halo comes from the two
+                neighbouring ranks over NVLink peer memory (peer.PeerHalo).
   order stats   local histograms over OWNED planes only, all-reduced (int64 sum) between
                 the hist and pick kernels of each of the 5 radix rounds: exact.
   AF3 encode    atoms are replicated (a few MB); each rank rasterises its slab + halo.
@@ -53,7 +55,7 @@ class SlabPlan:
     """Pure host arithmetic of the partition (unit-tested on CPU)."""
 
     def __init__(self, src_shape, voxel_size_xyz, grid_size, padding, world, target_voxel_size=1.0,
-                 halo_k=16, order=3):
+                 halo_k=16, order=3, aligned=True):
         self.src_shape = tuple(int(v) for v in src_shape)
         self.world = int(world)
         self.grid_size, self.padding, self.halo_k, self.order = int(grid_size), int(padding), int(halo_k), order
@@ -86,6 +88,11 @@ class SlabPlan:
             else:
                 src_lo = max(0, int(np.floor(ext_lo * scale)) - taps_lo - k)
                 src_hi = min(sz, int(np.floor((ext_hi - 1) * scale)) + taps_hi + k + 1)
+                if order == 3 and aligned:
+                    # whole prefilter segments + their windows: the slab's coefficients are then computed
+                    # from the same windows as on one GPU, i.e. the N-rank map is bit-identical to it
+                    a_lo, a_hi = ops.resample_slab_source_planes(sz, nz, ext_lo, ext_hi - ext_lo)
+                    src_lo, src_hi = min(src_lo, a_lo), max(src_hi, a_hi)
             self.ranks.append(RankSlab(out_lo, out_hi, ext_lo, ext_hi, src_lo, src_hi, ob[r], ob[r + 1]))
 
     def transfers(self, rank):

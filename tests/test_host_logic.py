@@ -85,6 +85,30 @@ def test_bench_plans_need_only_the_direct_neighbours(src, voxel, gs, pad, world)
             assert s_hi[1] == me.own_hi
 
 
+@pytest.mark.parametrize('src,voxel,gs,pad', [((679, 8, 8), 1.06, 48, 8), ((400, 8, 8), 1.2, 32, 16),
+                                             ((3200, 8, 8), 1.2, 32, 16), ((333, 8, 8), 0.9, 48, 8)])
+@pytest.mark.parametrize('world', [2, 3, 8])
+def test_slab_blocks_hold_whole_prefilter_windows(src, voxel, gs, pad, world):
+    """Bit-identity of the N-rank map rests on this: the z prefilter cuts a line into segments of
+    ceil(n / ceil(n / 26)) samples with a window of 16 before and 26 + 16 from the segment start (resample.cu,
+    cols_reg_kernel); a rank's block must contain the window of every segment that holds a plane its taps read."""
+    plan = SlabPlan(src, (np.float32(voxel),) * 3, gs, pad, world)
+    sz, nz = src[0], plan.out_shape[0]
+    n_seg = -(-sz // 26)
+    seg = -(-sz // n_seg)
+    scale = (sz - 1) / (nz - 1)
+    for me in plan.ranks:
+        if me.out_hi <= me.out_lo:
+            continue
+        lo_tap = max(0, int(np.floor(me.ext_lo * scale)) - 1)
+        hi_tap = min(sz - 1, int(np.floor((me.ext_hi - 1) * scale)) + 2)
+        for s in range(lo_tap // seg, hi_tap // seg + 1):
+            assert me.src_lo <= max(0, s * seg - 16) and me.src_hi >= min(sz, s * seg + 26 + 16), (me, s)
+        assert me.src_hi - me.src_lo <= (hi_tap - lo_tap + 1) + 2 * (16 + seg) + 4      # and not much more than that
+    loose = SlabPlan(src, (np.float32(voxel),) * 3, gs, pad, world, aligned=False)
+    assert all(a.src_lo <= b.src_lo and a.src_hi >= b.src_hi for a, b in zip(plan.ranks, loose.ranks))
+
+
 def test_far_halos_are_reported_so_the_caller_falls_back():
     plan = SlabPlan((160, 8, 8), (np.float32(1.1),) * 3, 32, 16, 8)           # blocks thinner than the halo
     assert any(PeerHalo.neighbour_plan(plan, r) is None for r in range(8))
