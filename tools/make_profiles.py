@@ -66,10 +66,16 @@ head = ['ncu --set full --clock-control none --import-source on, one launch per 
 open(f'{out_dir}/{prefix}_ncu_final.txt', 'w').write('\n'.join(head + ['== ' + b.rstrip() + '\n' for _, b in seen.values()]))
 
 # ---- traffic of the dominant kernel
-m = re.search(r'postproc_stitch_kernel.*?gpu__time_duration.sum\s+([\d.]+) us.*?dram__bytes_read.sum\s+([\d.]+) Mbyte.*?'
-              r'dram__bytes_write.sum\s+([\d.]+) Mbyte',
-              next(v for k, v in seen.items() if 'postproc_stitch_kernel' in k)[1], re.S)
-us, rd, wr = (float(v) for v in m.groups())
+blk = next(v for k, v in seen.items() if 'postproc_stitch_kernel' in k)[1]
+_scale = {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}
+
+
+def _metric(name):                     # -> MB for byte counters, us for durations
+    v, unit = re.search(name.replace('.', r'\.') + r'\s+([\d.]+)\s+(\w+)', blk).groups()
+    return float(v) * _scale[unit]
+
+
+us, rd, wr = _metric('gpu__time_duration.sum'), _metric('dram__bytes_read.sum'), _metric('dram__bytes_write.sum')
 alg = B * S ** 3 * 208
 json.dump({'postproc_stitch_kernel': {
     'dram_bytes_per_launch': (rd + wr) * 1e6, 'dram_read_bytes': rd * 1e6, 'dram_write_bytes': wr * 1e6,
