@@ -336,7 +336,9 @@ def make_measure(ctx):
         warmup = args.warmup if warmup is None else warmup
         vols = None
         for _ in range(warmup):
-            vols = pipe.run(src, header, atoms, model_fn, vols)      # checked at once: a broken setup fails here
+            # next_src: a stream of maps -- a z-slab rank exchanges the next map's source halo under this map's
+            # cube loop (one exchange per step either way; no-op on one GPU)
+            vols = pipe.run(src, header, atoms, model_fn, vols, next_src=src)      # checked at once: a broken setup fails here
         sync()
         timer = StageTimer(only)
         pipe.timer = timer
@@ -351,7 +353,7 @@ def make_measure(ctx):
         for _ in range(steps):
             # status words go to pinned memory in stream order and are checked after the loop (finish()):
             # no host synchronisation between the maps of the stream
-            vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True)
+            vols = pipe.run(src, header, atoms, model_fn, vols, defer_check=True, next_src=src)
         ev1.record()
         t_host = (time.perf_counter() - t_host) / steps * 1e3      # host time spent enqueueing one step
         sync()
@@ -421,6 +423,9 @@ def strong_720(ctx, identity):
         'stage_ms_per_step_rank0': stage_table(stages_all, steps),
         'bytes_moved_frac_of_peak': nbytes / world / (ms * 1e-3) / 1e9 / peak,
         'halo_exchange': getattr(pipe, 'halo_exchange', None), 'hist_exchange': getattr(pipe, 'hist_exchange', None),
+        'halo_prefetch': ('the source halo of map k+1 is exchanged on a side stream under the cube loop of map k '
+                          '(SlabPipeline.prefetch_source): one exchange per timed step, off the critical path'
+                          if world > 1 else None),
     }
     del vols
     # ---- parity: N-rank slab run == whole-map run on one GPU (same deterministic pointwise model)

@@ -177,12 +177,17 @@ class PeerHalo(_IpcGroup):
                                      self.epoch, self.slot_elems, C.c_void_p(self.status.data_ptr()),
                                      self._stream(stream)), 'halo_pull')
 
-    def exchange(self, own: torch.Tensor, plan) -> torch.Tensor:
-        """Assemble source planes [src_lo, src_hi): own part by a device copy, the rest from the neighbours."""
+    def exchange(self, own: torch.Tensor, plan, buf: torch.Tensor | None = None) -> torch.Tensor:
+        """Assemble source planes [src_lo, src_hi): own part by a device copy, the rest from the neighbours.
+        ``buf``: a caller-owned buffer of that shape (a new one otherwise)."""
         me = plan.ranks[self.rank]
         n = max(0, me.src_hi - me.src_lo)
         self.publish(own, plan)
-        buf = torch.empty((n,) + tuple(own.shape[1:]), dtype=own.dtype, device=own.device)
+        shape = (n,) + tuple(own.shape[1:])
+        if buf is None:
+            buf = torch.empty(shape, dtype=own.dtype, device=own.device)
+        elif tuple(buf.shape) != shape or buf.dtype != own.dtype or not buf.is_contiguous():
+            raise _lib.MicaError(f'halo buffer has shape {tuple(buf.shape)}, expected {shape}')
         lo, hi = max(me.src_lo, me.own_lo), min(me.src_hi, me.own_hi)
         if hi > lo:
             buf[lo - me.src_lo:hi - me.src_lo].copy_(own[lo - me.own_lo:hi - me.own_lo])

@@ -484,18 +484,26 @@ class MapPipeline:
 
     # ------------------------------------------------------------------ whole path
     @_on_device
-    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False, **predict_kw):
+    def prefetch_source(self, next_src, header=None):
+        """Hint: ``next_src`` is the map the next ``run`` will be given.  One GPU has nothing to fetch; a
+        z-slab rank exchanges the next map's source halo under this map's cube loop (SlabPipeline)."""
+
+    def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False, next_src=None,
+            **predict_kw):
         """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
         device tensors or None.  Raises on the reference's normalisation failures -- at once, or,
         with ``defer_check``, from ``finish()``: the status words are copied to pinned memory in
         stream order and the host does not wait, so the next map can be enqueued while this one
         still runs (a stream of maps; per-step host synchronisation also re-aligns the ranks of
-        a multi-GPU run at the cost of their host jitter)."""
+        a multi-GPU run at the cost of their host jitter).  ``next_src``: the source of the map that
+        follows (same header), already resident -- see ``prefetch_source``."""
         self.resample_and_normalize(src, header, defer_status=True)
         if atoms is not None:
             self.encode_af3(*atoms, defer_status=True)
         else:
             self.af3, self._atoms_binned = None, False
+        if next_src is not None:
+            self.prefetch_source(next_src, header)
         vols = self.predict_and_stitch(model_fn, vols, on_batch, **predict_kw)       # model_batch / d8 / order
         if defer_check:
             if self._pinned_free:

@@ -153,6 +153,9 @@ class SlabPipeline(MapPipeline):
             raise MicaError(f'halo_exchange must be peer or nccl, got {halo_exchange!r}')
         self.halo_exchange = halo_exchange
         self.peer_halo = None
+        self._halo_stream = None
+        self._halo_bufs, self._halo_turn = None, 0
+        self._prefetched = None
         self._plan_key = None
         #: 'peer' = one fused publish/signal/wait/sum kernel over NVLink peer memory per radix round
         #: (peer.PeerHistogram, built on first use); 'nccl' = torch.distributed.all_reduce
@@ -184,7 +187,46 @@ class SlabPipeline(MapPipeline):
             planes = max([planes] + [rng[1] - rng[0] for rng in np_ if rng is not None])
         return planes * plan.src_shape[1] * plan.src_shape[2]
 
+    def prefetch_source(self, next_own, header=None):
+        """Exchange the source halo of the NEXT map now, on a side stream, so that it runs under this map's
+        cube loop instead of at the head of the next step (publish never waits; the pull's wait for the
+        neighbour then costs nothing on the main stream).  Call it after this map's pre-phase has been
+        enqueued -- ``run(..., next_src=)`` does -- on EVERY rank, with the block the next ``run`` /
+        ``slab_resample`` will be given; the block must stay untouched until then.  A next call with another
+        block simply exchanges again.  No-op for plans the peer-memory exchange does not serve."""
+        if self.world == 1 or self.halo_exchange != 'peer' or self.peer_halo is None:
+            return                                    # the first map builds the exchange group (a collective)
+        if header is not None:
+            self.header = header
+        plan = self.make_plan(tuple(next_own.shape), self.header)
+        need = self._halo_slot_elems(plan)
+        if need is None or self.peer_halo.slot_elems < need:
+            return
+        if self._halo_stream is None:
+            self._halo_stream = torch.cuda.Stream(self.device)
+        main = torch.cuda.current_stream(self.device)
+        # two assembled-source buffers owned by the pipeline, used in turn: the one map k is being resampled
+        # from is next written by the prefetch of map k+2, which this stream wait orders behind map k+1's
+        # pre-phase (no allocator traffic between streams, no record_stream)
+        me = plan.ranks[self.rank]
+        shape = (max(0, me.src_hi - me.src_lo),) + tuple(next_own.shape[1:])
+        if self._halo_bufs is None or tuple(self._halo_bufs[0].shape) != shape:
+            main.wait_stream(self._halo_stream)        # a dropped prefetch may still be writing the old pair
+            self._halo_bufs = [torch.empty(shape, dtype=torch.float32, device=self.device) for _ in range(2)]
+        self._halo_turn ^= 1
+        buf = self._halo_bufs[self._halo_turn]
+        self._halo_stream.wait_stream(main)
+        with torch.cuda.stream(self._halo_stream):
+            self.peer_halo.exchange(next_own, plan, buf)
+            ev = torch.cuda.Event()
+            ev.record(self._halo_stream)
+        self._prefetched = ((next_own.data_ptr(), tuple(next_own.shape), next_own._version, self._plan_key), buf, ev)
+
     def _exchange(self, own):
+        pf, self._prefetched = self._prefetched, None
+        if pf is not None and pf[0] == (own.data_ptr(), tuple(own.shape), own._version, self._plan_key):
+            torch.cuda.current_stream(self.device).wait_event(pf[2])
+            return pf[1]
         if self.halo_exchange == 'peer' and self.world > 1:
             need = self._halo_slot_elems(self.plan)      # the same on every rank (the plan is global)
             if need is not None:

@@ -179,6 +179,54 @@ def test_peer_memory_halo_exchange_assembles_the_source_planes(cuda, world):
     groups[0].close()
 
 
+def test_next_map_halo_prefetch_is_consumed_and_bit_identical(cuda):
+    """SlabPipeline.prefetch_source: the halo of map k+1 is exchanged on a side stream while map k is still
+    in flight; the next slab_resample must take that buffer (no second exchange) and produce the planes of the
+    whole-map resample bit for bit (aligned plan, fast path).  A prefetch for a block that is not the one that
+    follows is dropped and the exchange runs again.  Two emulated ranks on their own streams."""
+    from mica_b200.peer import PeerHalo
+    world, src_shape, voxel = 2, (208, 96, 100), 1.1
+    hdr = MapHeader(voxel_size=(np.float32(voxel),) * 3)
+    plan = SlabPlan(src_shape, hdr.voxel_size, 48, 8, world)
+    plane = src_shape[1] * src_shape[2]
+    need = max(b - a for r in range(world) for rng in PeerHalo.neighbour_plan(plan, r) if rng is not None
+               for a, b in [rng])
+    groups = PeerHalo.emulate(cuda, world, need * plane)
+    calls = [0] * world
+    pipes = []
+    for r in range(world):
+        p = SlabPipeline(cuda, r, world, 48, 8, global_src_shape=src_shape, group=False)
+        p.peer_halo = groups[r]
+        real = groups[r].exchange
+
+        def counted(own, plan_, buf=None, *, real=real, r=r):
+            calls[r] += 1
+            return real(own, plan_, buf)
+        groups[r].exchange = counted
+        pipes.append(p)
+    streams = [torch.cuda.Stream(cuda) for _ in range(world)]
+    g = torch.Generator(device=cuda).manual_seed(11)
+    maps = [torch.rand(src_shape, generator=g, device=cuda) for _ in range(4)]
+    owns = [[m[me.own_lo:me.own_hi].contiguous() for me in plan.ranks] for m in maps]
+    want = [ops.resample(m, plan.out_shape) for m in maps]
+    torch.cuda.synchronize()
+    got = {}
+    # maps 0 -> 1 -> 2 with the next map announced; then map 3 although map 0 was announced (stale prefetch)
+    for k, nxt in ((0, 1), (1, 2), (2, 0), (3, None)):
+        for r, p in enumerate(pipes):
+            with torch.cuda.stream(streams[r]):
+                got[k, r], _ = p.slab_resample(owns[k][r], hdr)
+                if nxt is not None:
+                    p.prefetch_source(owns[nxt][r], hdr)
+    torch.cuda.synchronize()
+    assert calls == [5, 5]            # 0: exchange, 1 and 2: prefetched, 0 again: prefetched and dropped, 3: exchange
+    for (k, r), t in got.items():
+        me = plan.ranks[r]
+        assert not groups[r].timed_out()
+        assert torch.equal(t, want[k][me.ext_lo:me.ext_hi]), (k, r)
+    groups[0].close()
+
+
 def test_peer_halo_times_out_instead_of_hanging(cuda, monkeypatch):
     """A neighbour that never publishes turns into a status word after the bounded spin (MICA_PEER_TIMEOUT_MS;
     60 s by default -- ranks of a real job can be seconds apart)."""
