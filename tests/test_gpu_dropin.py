@@ -226,7 +226,10 @@ def test_reference_batching_reproduces_the_mixed_batches(cuda, tmp_path):
     assert good and rp.model.seen == [(3, False)]
     for k in ('backbone_probability', 'carbon_alpha_probability', 'amino_acid_probability'):
         assert np.abs(got[k] - want[k]).max() <= 1e-5, k
-    assert (got['amino_acid_prediction'] == want['amino_acid_prediction']).mean() > 0.9999
+    top2 = np.sort(want['amino_acid_probability'], axis=0)[-2:]
+    clear = (top2[1] - top2[0]) > 4e-6                             # equal wherever the top-2 gap is not rounding
+    same = got['amino_acid_prediction'] == want['amino_acid_prediction']
+    assert same[clear].all() and same.mean() > 0.9999
 
 
 def test_host_pool_and_all_four_volumes(cuda, tmp_path):
