@@ -13,6 +13,7 @@ preprocessing.py, create_grids.py, predict.py) are thin shells over this class.
 from __future__ import annotations
 
 import functools
+import os
 import time
 from contextlib import contextmanager
 from dataclasses import dataclass
@@ -483,11 +484,11 @@ class MapPipeline:
                 raise MicaError('AF3 encoding failed: atom index outside the grid (reference IndexError path, D7)')
 
     # ------------------------------------------------------------------ whole path
-    @_on_device
     def prefetch_source(self, next_src, header=None):
         """Hint: ``next_src`` is the map the next ``run`` will be given.  One GPU has nothing to fetch; a
         z-slab rank exchanges the next map's source halo under this map's cube loop (SlabPipeline)."""
 
+    @_on_device
     def run(self, src, header, atoms, model_fn, vols=None, on_batch=None, defer_check=False, next_src=None,
             **predict_kw):
         """map + atoms -> four stitched volumes (device).  ``atoms`` = (coords, bb_ch, aa_ch)
