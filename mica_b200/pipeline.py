@@ -13,7 +13,6 @@ preprocessing.py, create_grids.py, predict.py) are thin shells over this class.
 from __future__ import annotations
 
 import functools
-import os
 import time
 from contextlib import contextmanager
 from dataclasses import dataclass
