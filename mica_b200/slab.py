@@ -233,6 +233,13 @@ class SlabPipeline(MapPipeline):
                 from .peer import PeerHalo
                 if self.peer_halo is None or self.peer_halo.slot_elems < need:
                     if self.peer_halo is not None:
+                        # a neighbour may still be pulling from the old buffers (an exchange prefetched for a map
+                        # that never came): every rank takes this branch together, so wait for all of them
+                        torch.cuda.synchronize(self.device)
+                        if self.group is not False:
+                            import torch.distributed as dist
+                            if dist.is_available() and dist.is_initialized():
+                                dist.barrier(group=self.group)
                         self.peer_halo.close()
                     self.peer_halo = self._make_peer_halo(need)
                 return self.peer_halo.exchange(own, self.plan)
