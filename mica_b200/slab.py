@@ -193,12 +193,14 @@ class SlabPipeline(MapPipeline):
         neighbour then costs nothing on the main stream).  Call it after this map's pre-phase has been
         enqueued -- ``run(..., next_src=)`` does -- on EVERY rank, with the block the next ``run`` /
         ``slab_resample`` will be given; the block must stay untouched until then.  A next call with another
-        block simply exchanges again.  No-op for plans the peer-memory exchange does not serve."""
+        block simply exchanges again.  No-op for plans the peer-memory exchange does not serve and for a next
+        map of another geometry (shape, voxel size) than the current one."""
         if self.world == 1 or self.halo_exchange != 'peer' or self.peer_halo is None:
             return                                    # the first map builds the exchange group (a collective)
-        if header is not None:
-            self.header = header
-        plan = self.make_plan(tuple(next_own.shape), self.header)
+        header = self.header if header is None else header
+        if self.plan is None or self._plan_key_of(tuple(next_own.shape), header) != self._plan_key:
+            return                                    # another geometry: this map's plan must stay; exchanged in line
+        plan = self.plan
         need = self._halo_slot_elems(plan)
         if need is None or self.peer_halo.slot_elems < need:
             return
@@ -249,12 +251,16 @@ class SlabPipeline(MapPipeline):
         from .peer import PeerHalo
         return PeerHalo(self.device, self.rank, self.world, slot_elems, self.group)
 
-    def make_plan(self, own_shape, header):
+    def _plan_key_of(self, own_shape, header):
         gshape = self.global_src_shape
         if gshape is None:                      # weak-scaling default: equal blocks stacked along z
             gshape = (own_shape[0] * self.world, own_shape[1], own_shape[2])
-        key = (tuple(gshape), tuple(float(v) for v in header.voxel_size), self.grid_size, self.padding, self.world,
-               float(self.target_voxel_size), self.halo_k, self.order)
+        return (tuple(gshape), tuple(float(v) for v in header.voxel_size), self.grid_size, self.padding, self.world,
+                float(self.target_voxel_size), self.halo_k, self.order)
+
+    def make_plan(self, own_shape, header):
+        key = self._plan_key_of(own_shape, header)
+        gshape = key[0]
         if key != self._plan_key:               # host arithmetic only, but it runs once per map otherwise
             self.plan = SlabPlan(gshape, header.voxel_size, self.grid_size, self.padding, self.world,
                                  self.target_voxel_size, self.halo_k, self.order)
