@@ -109,6 +109,21 @@ def test_slab_blocks_hold_whole_prefilter_windows(src, voxel, gs, pad, world):
     assert all(a.src_lo <= b.src_lo and a.src_hi >= b.src_hi for a, b in zip(plan.ranks, loose.ranks))
 
 
+def test_aligned_plans_contain_the_loose_ones_for_any_shape():
+    """Random shapes / voxel sizes / geometries / rank counts: the segment-aligned block always contains the
+    16-plane-horizon block, stays inside the map, and the host entry point never refuses a slab the plan makes."""
+    rng = np.random.default_rng(1)
+    for _ in range(600):
+        sz, vox = int(rng.integers(4, 2200)), float(rng.uniform(0.45, 2.6))
+        gs, pad = [(32, 16), (48, 8), (16, 8)][int(rng.integers(3))]
+        world = int(rng.integers(1, 9))
+        tight = SlabPlan((sz, 8, 8), (np.float32(vox),) * 3, gs, pad, world)
+        loose = SlabPlan((sz, 8, 8), (np.float32(vox),) * 3, gs, pad, world, aligned=False)
+        for a, b in zip(tight.ranks, loose.ranks):
+            if a.out_hi > a.out_lo:
+                assert 0 <= a.src_lo <= b.src_lo and b.src_hi <= a.src_hi <= sz, (sz, vox, gs, pad, world, a, b)
+
+
 def test_far_halos_are_reported_so_the_caller_falls_back():
     plan = SlabPlan((160, 8, 8), (np.float32(1.1),) * 3, 32, 16, 8)           # blocks thinner than the halo
     assert any(PeerHalo.neighbour_plan(plan, r) is None for r in range(8))
